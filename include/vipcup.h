@@ -1,0 +1,89 @@
+/*
+ * vipcup.h -- C ABI of libvipcup.so: the B200 (sm_100a) implementation of the vip-cup-2022 inference hot
+ * path (preprocess -> backbone forward -> head / TTA / ensemble epilogue).
+ *
+ * The reference (awsaf49/vip-cup-2022) is pure Python/TensorFlow and has NO FFI of its own; the seams this
+ * library replaces are Python-level.  Each entry point cites the reference code whose
+ * arithmetic it takes over.  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VIP_ERR_* code; vip_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread; nothing throws
+ *     across the ABI.
+ *   - "device" pointers are CUDA device pointers on the current device; "host" pointers are ordinary (ideally
+ *     page-locked) host memory.  The caller owns every buffer it passes in; the library owns only what it
+ *     creates behind its handles (weights, workspaces).
+ *   - all device work is enqueued on the caller's stream (cudaStream_t passed as void*; NULL = legacy default
+ *     stream); no hidden synchronisation unless the function name ends in _host / _sync.
+ *   - handles are not thread-safe; use one handle per device / rank.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with VIP_ERR_CUDA.
+ */
+#ifndef VIPCUP_H_
+#define VIPCUP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIP_OK 0
+#define VIP_ERR_INVALID (-1)     /* bad argument (null pointer, size out of range, unknown name) */
+#define VIP_ERR_CUDA (-2)        /* CUDA runtime/driver error, message carries cudaGetErrorString */
+#define VIP_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels were built for */
+#define VIP_ERR_STATE (-4)       /* call order violated (e.g. forward before finalize) */
+
+#define VIP_DTYPE_F32 0
+#define VIP_DTYPE_BF16 1
+
+/* per-image flag bits for vip_preprocess (dataset/augment.py:115-120,142-146) */
+#define VIP_FLAG_HFLIP 1u /* tf.image.flip_left_right */
+#define VIP_FLAG_VFLIP 2u /* tf.image.flip_up_down    */
+#define VIP_FLAG_GRAY 4u  /* rgb_to_grayscale -> grayscale_to_rgb */
+
+/* library / build information ------------------------------------------------------------------ */
+const char* vip_version(void);
+const char* vip_last_error(void);
+/* number of kernels launched by this library on the calling thread since the last reset (bench.py's
+ * "gpu_launches" claim is read from here). */
+int64_t vip_launch_count(void);
+void vip_launch_count_reset(void);
+
+/* -------------------------------------------------------------------------------------------------
+ * Preprocessing.  Replaces, per image,
+ *   dataset/dataset.py:31-37   tf.cast(float32) -> tf.image.resize(bicubic) -> / 255.0
+ *   dataset/augment.py:110-113 tf.image.random_jpeg_quality  (quality decided by the caller)
+ *   dataset/augment.py:115-120 flip_left_right / flip_up_down
+ *   dataset/augment.py:142-146 rgb_to_grayscale -> grayscale_to_rgb
+ * and the "slice then resize" random-crop semantic of
+ *   models/keras_cv_attention_models/imagenet/data.py:56-63.
+ * Order: crop -> bicubic(Hc x Wc -> Ho x Wo) -> /255 -> [JPEG round trip at quality q] -> flips -> gray.
+ *
+ *   src        device u8  [N, Hs, Ws, 3] NHWC (decoded RGB)
+ *   crop_yxhw  device i32 [N, 4] (y0, x0, h, w) inside the source, or NULL for the full image
+ *   jpeg_q     device i32 [N], q in [1,100] enables the libjpeg 4:2:0 baseline encode->decode emulation,
+ *              q < 0 skips it; NULL skips it for every image
+ *   flags      device u8  [N] VIP_FLAG_* bits, or NULL
+ *   dst        device f32 or bf16 [N, Ho, Wo, 3] NHWC
+ * Limits: 1 <= Ws <= 1024; Ho, Wo <= 256 when any image uses JPEG emulation (plane residency in shared
+ * memory), otherwise Ho, Wo <= 1024.  Results are bit-identical to oracle/preprocess.py.
+ */
+int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const int32_t* crop_yxhw, const int32_t* jpeg_q,
+                   const uint8_t* flags, int Ho, int Wo, void* dst, int dst_dtype, void* cuda_stream);
+
+/* Same operation on HOST buffers: copies inputs host->device, runs vip_preprocess in chunks on internal
+ * streams so that copies overlap compute, copies the result device->host and synchronises before returning.
+ * This is the call that stands where dataset.build_dataset (dataset/dataset.py:64-102) hands a batch to the
+ * caller.  use_jpeg: 0 = jpeg_q ignored. */
+int vip_preprocess_host(const uint8_t* src, int N, int Hs, int Ws, const int32_t* crop_yxhw, const int32_t* jpeg_q,
+                        const uint8_t* flags, int Ho, int Wo, void* dst, int dst_dtype);
+
+/* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
+ * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */
+int vip_selftest_div255(uint64_t* mismatches, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIPCUP_H_ */

@@ -1,0 +1,63 @@
+"""ctypes binding of libvipcup.so -- the only way Python reaches the kernels (no torch types cross the ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvipcup.so")
+
+VIP_DTYPE_F32, VIP_DTYPE_BF16 = 0, 1
+FLAG_HFLIP, FLAG_VFLIP, FLAG_GRAY = 1, 2, 4
+
+
+class VipError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/vipcup.h declares (tests check this)
+SIGNATURES = {
+    "vip_version": (C.c_char_p, []),
+    "vip_last_error": (C.c_char_p, []),
+    "vip_launch_count": (C.c_int64, []),
+    "vip_launch_count_reset": (None, []),
+    "vip_preprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "vip_preprocess_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "vip_selftest_div255": (C.c_int, [C.POINTER(C.c_uint64), C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libvipcup.so (built by ``__graft_entry__.build()`` / ``python -m vipcup_b200.build``). Fails loudly."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VipError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vip_last_error().decode("utf-8", "replace")
+        raise VipError(f"{what or 'libvipcup'} failed with code {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(lib().vip_launch_count())
+
+
+def launch_count_reset() -> None:
+    lib().vip_launch_count_reset()
