@@ -408,7 +408,7 @@ def synth_image(i: int, h: int = 200, w: int = 200) -> np.ndarray:
     grad = np.linspace(0, rng.uniform(0.0, 0.3), w)[None, :, None]
     img = img * 0.8 + noise + grad
     img = (img - img.min()) / (img.max() - img.min() + 1e-9)
-    return np.clip(img * 255.0 + 0.5, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(img * 255.0 + 0.5, 0, 255).astype(np.uint8))
 
 
 def synth_decisions(n: int, seed: int = 42, src_h: int = 200, src_w: int = 200):
