@@ -65,6 +65,8 @@ def test_jpeg_golden_vectors_from_libjpeg_turbo(cuda_device):
     dict(hs=64, ws=64, ho=256, wo=256, n=3, crop=True, jpeg=True, flags=True),       # maximum JPEG plane size
     dict(hs=31, ws=17, ho=9, wo=7, n=5, crop=False, jpeg=True, flags=True),          # smaller than one MCU row pair
     dict(hs=300, ws=260, ho=200, wo=200, n=4, crop=True, jpeg=False, flags=True),    # other source sizes (dataset.py:33)
+    dict(hs=5, ws=4, ho=1, wo=2, n=3, crop=False, jpeg=True, flags=True),            # degenerate: one chroma sample
+    dict(hs=33, ws=35, ho=40, wo=24, n=4, crop=True, jpeg=True, flags=True),         # row pitch not a multiple of 4 (byte staging)
 ])
 def test_parity_with_oracle(cuda_device, case):
     from oracle import preprocess as P

@@ -19,6 +19,8 @@
 //   C  fancy chroma upsampling, YCbCr->RGB, *1/255, flips / gray, vectorised stores
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vip {
@@ -38,8 +40,10 @@ struct PreArgs {
   int N, Hs, Ws, Ho, Wo;
   int hc, wc;              // real chroma size ceil(Ho/2), ceil(Wo/2)
   int HpY, WpY, HpC, WpC;  // padded plane sizes (multiples of 8)
-  int v_pitch;             // floats per stripe row (= Ws * 3)
-  int off_wy, off_iy, off_wx, off_ix, off_qt, off_Y, off_Cb, off_Cr, off_v;  // smem byte offsets
+  int v_pitch;             // floats per stripe row (= 3 * Ws rounded up to 4 pixels)
+  int src_pitch;           // bytes per staged source row
+  int word_path;           // 1: every source row is 4-byte aligned -> cp.async word staging
+  int off_wy, off_iy, off_wx, off_ix, off_qt, off_Y, off_Cb, off_Cr, off_src, off_v;  // smem byte offsets
 };
 
 __constant__ uint8_t c_luma_base[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
@@ -191,8 +195,6 @@ __device__ __forceinline__ void idct8(int (&d)[8]) {
   d[4] = (t13 - t0) >> n;
 }
 
-__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
-
 // 8x8 transpose across the 8 lanes of a block group through a per-warp smem scratch.
 __device__ __forceinline__ void transpose8(int (&d)[8], int* scr, int b, int r) {
   int4* wp = reinterpret_cast<int4*>(scr + b * kTrStride + r * 8);
@@ -283,6 +285,22 @@ __device__ __forceinline__ void emit_quad(void* img, size_t e0, int Ho, int Wo, 
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// floor(i / d) for 0 <= i, i * d < 2^32: multiply by ceil(2^32 / d) and keep the high word (d == 1 passes through)
+struct FastDiv {
+  unsigned m;
+  int d;
+  __device__ __forceinline__ explicit FastDiv(int d_) : m(0xffffffffu / (unsigned)d_ + 1u), d(d_) {}
+  __device__ __forceinline__ int div(int i) const { return d == 1 ? i : (int)__umulhi((unsigned)i, m); }
+};
+
+__device__ __forceinline__ float u8f(unsigned word, int k) { return (float)((word >> (8 * k)) & 0xffu); }
+
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -294,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
   uint8_t* s_Y = smem + a.off_Y;
   uint8_t* s_Cb = smem + a.off_Cb;
   uint8_t* s_Cr = smem + a.off_Cr;
+  uint8_t* s_src = smem + a.off_src;
   float* s_v = reinterpret_cast<float*>(smem + a.off_v);
 
   const int tid = threadIdx.x;
@@ -310,8 +329,11 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
   const int q = (a.jq != nullptr) ? a.jq[n] : -1;
   const bool jpeg = q >= 0;
   const unsigned flags = (a.flags != nullptr) ? a.flags[n] : 0u;
-  const size_t row_pitch = (size_t)a.Ws * 3;
+  const int row_pitch = a.Ws * 3;
+  // first byte of the crop; with word_path every source row starts 4-byte aligned, so only x0 misaligns it
   const uint8_t* src = a.src + (size_t)n * a.Hs * row_pitch + (size_t)y0 * row_pitch + (size_t)x0 * 3;
+  const int mis = a.word_path ? ((x0 * 3) & 3) : 0;
+  const int w3 = w * 3;
   void* dst = a.dst;
   const size_t e0 = (size_t)n * Ho * Wo * 3;
 
@@ -331,36 +353,87 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
   __syncthreads();
 
   const int hc = a.hc, wc = a.wc;
-  const int w3 = w * 3;
   const int WqC = jpeg ? a.WpC : wc;  // quad columns (JPEG planes need the right-edge padding)
+  const FastDiv div_q(WqC);
+  const int G = (w + 3) >> 2;                                   // 4-pixel groups per source row
+  const FastDiv div_g(G);
+  const unsigned fsel = 0x3210u + 0x1111u * (unsigned)mis;       // byte funnel: drop the `mis` leading bytes
+
+  // stages the source rows [lo, hi] of the crop that the stripe starting at output row oy0 reads
+  auto stage_rows = [&](int oy0) {
+    const int rows = min(kStripe, Ho - oy0);
+    const int lo = s_iy[oy0].x, hi = s_iy[oy0 + rows - 1].w;
+    const int nrows = hi - lo + 1;
+    if (a.word_path) {
+      const int nwords = (mis + w3 + 3) >> 2;
+      const FastDiv div_w(nwords);
+      const uint8_t* g0 = src - mis + (size_t)lo * row_pitch;
+      for (int i = tid; i < nrows * nwords; i += kThreads) {
+        const int r = div_w.div(i);
+        const int j = i - r * nwords;
+        cp_async4(s_src + r * a.src_pitch + 4 * j, g0 + (size_t)r * row_pitch + 4 * j);
+      }
+    } else {
+      const FastDiv div_b(w3);
+      const uint8_t* g0 = src + (size_t)lo * row_pitch;
+      for (int i = tid; i < nrows * w3; i += kThreads) {
+        const int r = div_b.div(i);
+        const int j = i - r * w3;
+        s_src[r * a.src_pitch + j] = __ldg(g0 + (size_t)r * row_pitch + j);
+      }
+    }
+  };
+
+  stage_rows(0);
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- phase A
   for (int cy0 = 0; cy0 < hc; cy0 += kStripe / 2) {
     const int oy0 = 2 * cy0;
     const int rows = min(kStripe, Ho - oy0);  // real rows in this stripe
-    // A2: vertical taps, one source column-channel per thread
-    for (int xc = tid; xc < w3; xc += kThreads) {
-      const uint8_t* col = src + xc;
-      for (int r = 0; r < rows; ++r) {
+    // A2: vertical taps; one item = (stripe row, group of 4 source pixels = 12 bytes = 3 words after the funnel)
+    {
+      const int lo = s_iy[oy0].x;
+      for (int it = tid; it < rows * G; it += kThreads) {
+        const int r = div_g.div(it);
+        const int g = it - r * G;
         const float4 wy = s_wy[oy0 + r];
         const short4 iy = s_iy[oy0 + r];
-        const float p0 = (float)__ldg(col + iy.x * row_pitch);
-        const float p1 = (float)__ldg(col + iy.y * row_pitch);
-        const float p2 = (float)__ldg(col + iy.z * row_pitch);
-        const float p3 = (float)__ldg(col + iy.w * row_pitch);
-        s_v[r * a.v_pitch + xc] = tap4(p0, p1, p2, p3, wy);
+        const uint8_t* base = s_src + 12 * g;
+        const unsigned* t0 = reinterpret_cast<const unsigned*>(base + (iy.x - lo) * a.src_pitch);
+        const unsigned* t1 = reinterpret_cast<const unsigned*>(base + (iy.y - lo) * a.src_pitch);
+        const unsigned* t2 = reinterpret_cast<const unsigned*>(base + (iy.z - lo) * a.src_pitch);
+        const unsigned* t3 = reinterpret_cast<const unsigned*>(base + (iy.w - lo) * a.src_pitch);
+        unsigned A[4], B[4], C[4], D[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { A[k] = t0[k]; B[k] = t1[k]; C[k] = t2[k]; D[k] = t3[k]; }
+        float o[12];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const unsigned wa = __byte_perm(A[j], A[j + 1], fsel), wb = __byte_perm(B[j], B[j + 1], fsel);
+          const unsigned wc_ = __byte_perm(C[j], C[j + 1], fsel), wd = __byte_perm(D[j], D[j + 1], fsel);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[4 * j + k] = tap4(u8f(wa, k), u8f(wb, k), u8f(wc_, k), u8f(wd, k), wy);
+        }
+        float4* vp = reinterpret_cast<float4*>(s_v + r * a.v_pitch + 12 * g);
+        vp[0] = make_float4(o[0], o[1], o[2], o[3]);
+        vp[1] = make_float4(o[4], o[5], o[6], o[7]);
+        vp[2] = make_float4(o[8], o[9], o[10], o[11]);
       }
     }
     __syncthreads();
-    // A3: horizontal taps per 2x2 quad
+    if (cy0 + kStripe / 2 < hc) stage_rows(oy0 + kStripe);  // async: lands while A3 runs
+    // A3: horizontal taps per 2x2 quad, /255, quantise, colour convert
     const int nq = (kStripe / 2) * WqC;
     for (int qi = tid; qi < nq; qi += kThreads) {
-      const int qr = qi / WqC;
+      const int qr = div_q.div(qi);
       const int cx = qi - qr * WqC;
       const int cy = cy0 + qr;
       if (cy >= hc) continue;
       float fv[2][2][3];
       int cbs = 0, crs = 0;
+      unsigned ypk[2] = {0u, 0u};
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const int ox = min(2 * cx + dx, Wo - 1);
@@ -370,10 +443,14 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
         for (int dy = 0; dy < 2; ++dy) {
           const int rr = min(2 * qr + dy, rows - 1);
           const float* vr = s_v + rr * a.v_pitch;
+          const float* p0 = vr + ix.x * 3;
+          const float* p1 = vr + ix.y * 3;
+          const float* p2 = vr + ix.z * 3;
+          const float* p3 = vr + ix.w * 3;
           int rgb[3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float val = tap4(vr[ix.x * 3 + c], vr[ix.y * 3 + c], vr[ix.z * 3 + c], vr[ix.w * 3 + c], wx);
+            const float val = tap4(p0[c], p1[c], p2[c], p3[c], wx);
             const float f = div255(val);
             fv[dy][dx][c] = f;
             // tf.image.convert_image_dtype(float -> uint8, saturate=True): trunc(clip(f * 255.5, 0, 255))
@@ -384,12 +461,15 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
             const int Y = (19595 * rgb[0] + 38470 * rgb[1] + 7471 * rgb[2] + 32768) >> 16;
             cbs += (-11059 * rgb[0] - 21709 * rgb[1] + 32768 * rgb[2] + (128 << 16) + 32767) >> 16;
             crs += (32768 * rgb[0] - 27439 * rgb[1] - 5329 * rgb[2] + (128 << 16) + 32767) >> 16;
-            const int yy = 2 * cy + dy, xx = 2 * cx + dx;
-            if (xx < a.WpY) s_Y[yy * a.WpY + xx] = (uint8_t)Y;
+            ypk[dy] |= (unsigned)Y << (8 * dx);
           }
         }
       }
       if (jpeg) {
+        if (2 * cx < a.WpY) {   // WpY is even: both pixels of the pair are inside or both outside
+          *reinterpret_cast<unsigned short*>(s_Y + (2 * cy) * a.WpY + 2 * cx) = (unsigned short)ypk[0];
+          *reinterpret_cast<unsigned short*>(s_Y + (2 * cy + 1) * a.WpY + 2 * cx) = (unsigned short)ypk[1];
+        }
         const int bias = 1 + (cx & 1);  // jcsample.c h2v2_downsample: 1,2,1,2,...
         s_Cb[cy * a.WpC + cx] = (uint8_t)((cbs + bias) >> 2);
         s_Cr[cy * a.WpC + cx] = (uint8_t)((crs + bias) >> 2);
@@ -397,6 +477,7 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
         emit_quad<kBf16>(dst, e0, Ho, Wo, cy, cx, flags, fv);
       }
     }
+    cp_async_wait_all();
     __syncthreads();
   }
   if (!jpeg) return;
@@ -423,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
     int* scr = reinterpret_cast<int*>(s_v) + warp * (4 * kTrStride);
     const int nbxY = a.WpY >> 3, nbY = (a.HpY >> 3) * nbxY;
     const int nbxC = a.WpC >> 3, nbC = (a.HpC >> 3) * nbxC;
+    const FastDiv div_bY(nbxY), div_bC(nbxC);
     const int itY = (nbY + 3) >> 2, itC = (2 * nbC + 3) >> 2;
     int cur = -1;
     int qt[8], qm[8];
@@ -441,17 +523,20 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
       const bool live = bi < nb;
       bi = live ? bi : nb - 1;
       uint8_t* plane;
-      int pitch, nbx;
+      int pitch, by;
       if (comp == 0) {
-        plane = s_Y; pitch = a.WpY; nbx = nbxY;
+        plane = s_Y; pitch = a.WpY;
+        by = div_bY.div(bi);
+        bi -= by * nbxY;
       } else {
         const bool second = bi >= nbC;
         plane = second ? s_Cr : s_Cb;
         bi -= second ? nbC : 0;
-        pitch = a.WpC; nbx = nbxC;
+        pitch = a.WpC;
+        by = div_bC.div(bi);
+        bi -= by * nbxC;
       }
-      const int by = bi / nbx, bx = bi - by * nbx;
-      uint2* rowp = reinterpret_cast<uint2*>(plane + (by * 8 + r) * pitch + bx * 8);
+      uint2* rowp = reinterpret_cast<uint2*>(plane + (by * 8 + r) * pitch + bi * 8);
       const uint2 raw = *rowp;
       int d[8];
       d[0] = raw.x & 255; d[1] = (raw.x >> 8) & 255; d[2] = (raw.x >> 16) & 255; d[3] = raw.x >> 24;
@@ -470,8 +555,10 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
       transpose8(d, scr, b, r);       // lane r holds row y = r
       idct8<false>(d);
       uint2 o;
-      o.x = clamp255(d[0]) | (clamp255(d[1]) << 8) | (clamp255(d[2]) << 16) | (clamp255(d[3]) << 24);
-      o.y = clamp255(d[4]) | (clamp255(d[5]) << 8) | (clamp255(d[6]) << 16) | (clamp255(d[7]) << 24);
+      o.x = __vimin_s32_relu(d[0], 255) | (__vimin_s32_relu(d[1], 255) << 8) | (__vimin_s32_relu(d[2], 255) << 16) |
+            (__vimin_s32_relu(d[3], 255) << 24);
+      o.y = __vimin_s32_relu(d[4], 255) | (__vimin_s32_relu(d[5], 255) << 8) | (__vimin_s32_relu(d[6], 255) << 16) |
+            (__vimin_s32_relu(d[7], 255) << 24);
       if (live) *rowp = o;
     }
   }
@@ -480,37 +567,39 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
   // ---- phase C: fancy upsampling (jdsample.c h2v2_fancy_upsample), YCbCr->RGB (jdcolor.c), scale, store
   {
     const int nq = hc * wc;
+    const FastDiv div_c(wc);
     for (int qi = tid; qi < nq; qi += kThreads) {
-      const int cy = qi / wc, cx = qi - cy * wc;
-      const int cym = max(cy - 1, 0), cyp = min(cy + 1, hc - 1);
+      const int cy = div_c.div(qi);
+      const int cx = qi - cy * wc;
+      const int o_m = max(cy - 1, 0) * a.WpC, o_c = cy * a.WpC, o_p = min(cy + 1, hc - 1) * a.WpC;
       const int cxm = max(cx - 1, 0), cxp = min(cx + 1, wc - 1);
-      int ch[2][2][2];  // [comp][dy][dx] upsampled, centred
+      int ch[2][2][2];  // [comp][dy][dx] upsampled chroma (not centred)
 #pragma unroll
       for (int comp = 0; comp < 2; ++comp) {
         const uint8_t* P = comp ? s_Cr : s_Cb;
-        const uint8_t* r0 = P + cym * a.WpC;
-        const uint8_t* r1 = P + cy * a.WpC;
-        const uint8_t* r2 = P + cyp * a.WpC;
-        const int n_l = r1[cxm], n_c = r1[cx], n_r = r1[cxp];
+        const int n_l = P[o_c + cxm], n_c = P[o_c + cx], n_r = P[o_c + cxp];
         // row 2cy: nearest = cy, further = cy-1;  row 2cy+1: further = cy+1
-        const int u_l = 3 * n_l + r0[cxm], u_c = 3 * n_c + r0[cx], u_r = 3 * n_r + r0[cxp];
-        const int d_l = 3 * n_l + r2[cxm], d_c = 3 * n_c + r2[cx], d_r = 3 * n_r + r2[cxp];
-        ch[comp][0][0] = ((3 * u_c + u_l + 8) >> 4) - 128;
-        ch[comp][0][1] = ((3 * u_c + u_r + 7) >> 4) - 128;
-        ch[comp][1][0] = ((3 * d_c + d_l + 8) >> 4) - 128;
-        ch[comp][1][1] = ((3 * d_c + d_r + 7) >> 4) - 128;
+        const int u_l = 3 * n_l + P[o_m + cxm], u_c = 3 * n_c + P[o_m + cx], u_r = 3 * n_r + P[o_m + cxp];
+        const int d_l = 3 * n_l + P[o_p + cxm], d_c = 3 * n_c + P[o_p + cx], d_r = 3 * n_r + P[o_p + cxp];
+        ch[comp][0][0] = (3 * u_c + u_l + 8) >> 4;
+        ch[comp][0][1] = (3 * u_c + u_r + 7) >> 4;
+        ch[comp][1][0] = (3 * d_c + d_l + 8) >> 4;
+        ch[comp][1][1] = (3 * d_c + d_r + 7) >> 4;
       }
       float fv[2][2][3];
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
+        const int yy = min(2 * cy + dy, a.HpY - 1);
+        const int xx = min(2 * cx, a.WpY - 2);
+        const unsigned ypair = *reinterpret_cast<const unsigned short*>(s_Y + yy * a.WpY + xx);
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-          const int yy = min(2 * cy + dy, a.HpY - 1), xx = min(2 * cx + dx, a.WpY - 1);
-          const int Y = s_Y[yy * a.WpY + xx];
+          // R = Y + ((91881*cr' + 32768) >> 16) with cr' = cr - 128: fold Y and the -128 into one addend
+          const int yb = (int)(((ypair >> (8 * dx)) & 255u) << 16) + 32768;
           const int cb = ch[0][dy][dx], cr = ch[1][dy][dx];
-          const int R = clamp255(Y + ((91881 * cr + 32768) >> 16));
-          const int G = clamp255(Y + ((-22554 * cb - 46802 * cr + 32768) >> 16));
-          const int B = clamp255(Y + ((116130 * cb + 32768) >> 16));
+          const int R = __vimin_s32_relu((91881 * cr + (yb - 128 * 91881)) >> 16, 255);
+          const int G = __vimin_s32_relu((-22554 * cb - 46802 * cr + (yb + 128 * (22554 + 46802))) >> 16, 255);
+          const int B = __vimin_s32_relu((116130 * cb + (yb - 128 * 116130)) >> 16, 255);
           // convert_image_dtype(uint8 -> float32): cast * (1/255)
           fv[dy][dx][0] = __fmul_rn((float)R, 0.003921568859368562698f);
           fv[dy][dx][1] = __fmul_rn((float)G, 0.003921568859368562698f);
@@ -566,7 +655,11 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
   a.hc = (Ho + 1) / 2; a.wc = (Wo + 1) / 2;
   a.HpY = align_up(Ho, 8); a.WpY = align_up(Wo, 8);
   a.HpC = align_up(a.hc, 8); a.WpC = align_up(a.wc, 8);
-  a.v_pitch = Ws * 3;
+  a.v_pitch = align_up(Ws, 4) * 3;
+  a.src_pitch = align_up(align_up(Ws, 4) * 3 + 8, 16);
+  a.word_path = ((Ws * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) ? 1 : 0;
+  // source rows one stripe can touch: taps are monotonic, span <= ceil((kStripe-1) * Hs/Ho) + 4 rows (+1 slack)
+  const int src_rows = std::min(Hs, (int)(((long long)(kStripe - 1) * Hs + Ho - 1) / Ho) + 5);
   int off = 0;
   a.off_wy = off; off += Ho * 16;
   a.off_wx = off; off += Wo * 16;
@@ -579,6 +672,7 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
     a.off_Cb = off; off += align_up(a.HpC * a.WpC, 16);
     a.off_Cr = off; off += align_up(a.HpC * a.WpC, 16);
   }
+  a.off_src = off; off += align_up(src_rows * a.src_pitch, 16);
   a.off_v = off;
   int vbytes = kStripe * a.v_pitch * 4;
   const int scr_bytes = kWarps * 4 * kTrStride * 4;
