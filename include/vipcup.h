@@ -79,6 +79,15 @@ int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const int32_t* cro
 int vip_preprocess_host(const uint8_t* src, int N, int Hs, int Ws, const int32_t* crop_yxhw, const int32_t* jpeg_q,
                         const uint8_t* flags, int Ho, int Wo, void* dst, int dst_dtype);
 
+/* Raw bf16 contraction on the tcgen05 tensor cores (the building block of every Conv2D / Dense of the backbones:
+ * models/resnet_rs/resnet_rs_model.py:64-84, models/gcvit/layers/attention.py:25,33, models/gcvit/layers/feature.py:20-22):
+ *   out[M,N] = act(A[M,K] x B[N,K]^T + bias[N]) + residual[M,N]
+ * A, B, residual: device bf16, row-major (lda / ldb / ldr elements between rows, multiples of 8); bias device f32 or
+ * NULL; act: 0 none, 1 relu, 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).
+ * K % 8 == 0, N % 32 == 0. */
+int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
+                  const void* residual, int ldr, void* out, int ldc, int out_dtype, void* cuda_stream);
+
 /* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
  * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */
 int vip_selftest_div255(uint64_t* mismatches, void* cuda_stream);

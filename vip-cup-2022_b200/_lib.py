@@ -27,6 +27,8 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "vip_preprocess_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "vip_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vip_selftest_div255": (C.c_int, [C.POINTER(C.c_uint64), C.c_void_p]),
 }
 
