@@ -81,12 +81,45 @@ int vip_preprocess_host(const uint8_t* src, int N, int Hs, int Ws, const int32_t
 
 /* Raw bf16 contraction on the tcgen05 tensor cores (the building block of every Conv2D / Dense of the backbones:
  * models/resnet_rs/resnet_rs_model.py:64-84, models/gcvit/layers/attention.py:25,33, models/gcvit/layers/feature.py:20-22):
- *   out[M,N] = act(A[M,K] x B[N,K]^T + bias[N]) + residual[M,N]
- * A, B, residual: device bf16, row-major (lda / ldb / ldr elements between rows, multiples of 8); bias device f32 or
- * NULL; act: 0 none, 1 relu, 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).
- * K % 8 == 0, N % 32 == 0. */
+ *   out[M,N] = act(A[M,K] x B[N,K]^T + bias[N]) * colscale[N] + residual[M,N]
+ * A, B, residual: device bf16, row-major (lda / ldb / ldr elements between rows, multiples of 8); bias, colscale
+ * (GCViT layer-scale gamma, models/gcvit/layers/block.py:41-56,79-80): device f32 or NULL; act: 0 none, 1 relu,
+ * 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).  K % 8 == 0, N % 32 == 0. */
 int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
-                  const void* residual, int ldr, void* out, int ldc, int out_dtype, void* cuda_stream);
+                  const float* colscale, const void* residual, int ldr, void* out, int ldc, int out_dtype,
+                  void* cuda_stream);
+
+/* ---- layer kernels of the backbones; activations are device bf16 NHWC / [tokens, C], C % 8 == 0 ------------------ */
+/* Conv2D with explicit zero padding as an im2col matrix [N*Ho*Wo, Kp] (K order r,s,c = Keras kernel (kh,kw,Cin,Cout)
+ * flattened): models/resnet_rs/resnet_rs_model.py:64-84, model_utils.py:22-46; gcvit embedding.py:15, feature.py:98. */
+int vip_im2col_bf16(const void* x, int N, int H, int W, int C, int ksize, int stride, int pad, int Ho, int Wo, void* out,
+                    int Kp, void* cuda_stream);
+/* AveragePooling2D(2,2,'same'), divisor = valid count: models/resnet_rs/resnet_rs_model.py:207-212. out [N,ceil(H/2),ceil(W/2),C] */
+int vip_avgpool2_same_bf16(const void* x, int N, int H, int W, int C, void* out, void* cuda_stream);
+/* GlobalAveragePooling2D [N,HW,C] -> [N,C] as bf16 and/or f32 (either may be NULL): resnet_rs_model.py:149,469; gcvit.py:81; feature.py:55 */
+int vip_global_avgpool_bf16(const void* x, int N, int HW, int C, void* out_bf16, float* out_f32, void* cuda_stream);
+/* out = act(y * gate[n,c] + shortcut); gate f32 [N,C] or NULL, shortcut bf16 or NULL, act 0 none / 1 relu:
+ * SE excite + Add + ReLU, resnet_rs_model.py:183,278-280; gcvit feature.py:66,109,150 */
+int vip_scale_add_act_bf16(const void* y, const float* gate, const void* shortcut, void* out, int N, int HW, int C, int act,
+                           void* cuda_stream);
+/* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79 */
+int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, long long M, int C, float eps,
+                       void* cuda_stream);
+/* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ exact GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134 */
+int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, int W, int C, int gelu, void* cuda_stream);
+/* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
+int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
+/* Window attention, head_dim 32, window partition/reverse folded into addressing: gcvit attention.py:52-83, window.py:3-14.
+ * qkv bf16 [B*H*W, 3C] (local) or [B*H*W, 2C] = k,v (global, q_global bf16 [B, ws*ws, C] != NULL); rel_bias f32
+ * [heads, ws*ws, ws*ws] (table gathered by relative_position_index); out bf16 [B*H*W, C]. */
+int vip_window_attention_bf16(const void* qkv, const void* q_global, const float* rel_bias, void* out, int B, int H, int W,
+                              int C, int ws, int heads, void* cuda_stream);
+/* Classifier head on pooled f32 features [N,C]: Dense(k) (w f32 [C,k], b [k]) + softmax (sigmoid_head = 0) or sigmoid,
+ * probs f32 [N,k]; when acc != NULL also acc[n] += acc_weight * P(synthetic) with P = k > 1 ? 1 - probs[n,0] : probs[n,0]
+ * (TTA / fold / ensemble means of main.py:110-121,142 as one fused accumulation): resnet_rs_model.py:474-476, gcvit.py:88 */
+int vip_head_f32(const float* feat, const float* w, const float* b, float* probs, double* acc, double acc_weight, int N,
+                 int C, int k, int sigmoid_head, void* cuda_stream);
+int vip_cast_f32_bf16(const float* x, void* out, long long n, void* cuda_stream);
 
 /* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
  * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */

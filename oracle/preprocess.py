@@ -106,14 +106,14 @@ def resize_bicubic(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     out = v[:, ix[:, 0]] * wx[None, :, 0, None]
     for k in (1, 2, 3):
         out = out + v[:, ix[:, k]] * wx[None, :, k, None]
-    return out.astype(np.float32)
+    return np.ascontiguousarray(out, dtype=np.float32)
 
 
 def decode_to_float(u8_hwc: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     """dataset.py:31-37: cast -> resize (always runs, identity at equal size) -> IEEE ``/ 255.0``."""
     x = u8_hwc.astype(np.float32)
     x = resize_bicubic(x, out_h, out_w)
-    return (x / F32(255.0)).astype(np.float32)
+    return np.ascontiguousarray((x / F32(255.0)).astype(np.float32))
 
 
 # ----------------------------------------------------------------------------------------------

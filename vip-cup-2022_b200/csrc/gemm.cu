@@ -331,11 +331,12 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, 
 
 // C-ABI test / utility entry point (also usable by a host that wants the raw contraction).
 extern "C" int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
-                             int act, const void* residual, int ldr, void* out, int ldc, int out_dtype,
-                             void* cuda_stream) {
+                             int act, const float* colscale, const void* residual, int ldr, void* out, int ldc,
+                             int out_dtype, void* cuda_stream) {
   vip::GemmEpilogue e;
   e.bias = bias;
   e.act = act;
+  e.colscale = colscale;
   e.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   e.ldr = ldr;
   e.ldc = ldc;

@@ -1,0 +1,140 @@
+"""ResNet-RS forward on the B200 kernels.  Mirrors the constructors of the reference
+(``models/resnet_rs/__init__.py:3-11``, ``resnet_rs_model.py:329-567``): same layer names, same Keras weight layout in,
+BatchNorm folded into the bf16 GEMM weights at load time.
+
+Layer -> kernel:
+  Conv2DFixedPadding 1x1            tcgen05 GEMM directly on the NHWC activation            (nn.gemm)
+  Conv2DFixedPadding 3x3 (s1 / s2)  im2col view + tcgen05 GEMM, BN bias + ReLU in the epilogue (nn.conv2d)
+  AveragePooling2D 'same'           vip_avgpool2_same_bf16
+  SE                                vip_global_avgpool -> two batch-wide tcgen05 GEMMs (bias+relu / bias+sigmoid)
+  excite + Add + ReLU               vip_scale_add_act_bf16
+  head                              vip_global_avgpool (f32) -> vip_head_f32 (Dense + softmax|sigmoid [+ ensemble acc])
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import nn
+
+BLOCK_ARGS = {  # models/resnet_rs/block_args.py:1-44
+    50: [(64, 3), (128, 4), (256, 6), (512, 3)],
+    101: [(64, 3), (128, 4), (256, 23), (512, 3)],
+    152: [(64, 3), (128, 8), (256, 36), (512, 3)],
+    200: [(64, 3), (128, 24), (256, 36), (512, 3)],
+}
+BN_EPS = 1e-5
+
+
+def _fold_conv_bn(W, conv, bnorm, device):
+    """(kh,kw,Cin,Cout) kernel + BN stats -> bf16 [Cout, Kp] (K order r,s,c; Kp = K rounded up to 8) and f32 bias."""
+    k = np.asarray(W[conv + "/kernel"], dtype=np.float32)
+    g, b = np.asarray(W[bnorm + "/gamma"], np.float32), np.asarray(W[bnorm + "/beta"], np.float32)
+    m, v = np.asarray(W[bnorm + "/moving_mean"], np.float32), np.asarray(W[bnorm + "/moving_variance"], np.float32)
+    s = g / np.sqrt(v + BN_EPS)
+    co = k.shape[3]
+    w2 = (k * s[None, None, None, :]).reshape(-1, co).T  # [Cout, K]
+    kk = w2.shape[1]
+    kp = (kk + 7) // 8 * 8
+    wp = np.zeros((co, kp), np.float32)
+    wp[:, :kk] = w2
+    return (torch.from_numpy(wp).to(device).to(torch.bfloat16).contiguous(),
+            torch.from_numpy(b - m * s).to(device).contiguous())
+
+
+def _dense(W, name, device):
+    k = np.asarray(W[name + "/kernel"], np.float32)
+    k = k.reshape(-1, k.shape[-1])  # (1,1,Cin,Cout) -> (Cin,Cout)
+    return (torch.from_numpy(np.ascontiguousarray(k.T)).to(device).to(torch.bfloat16).contiguous(),
+            torch.from_numpy(np.asarray(W[name + "/bias"], np.float32)).to(device).contiguous())
+
+
+class ResNetRS:
+    def __init__(self, depth=50, input_shape=(200, 200, 3), classes=2, classifier_activation="softmax", first_strides=2,
+                 device="cuda"):
+        if depth not in BLOCK_ARGS:
+            raise ValueError(f"ResNetRS depth {depth} not supported")
+        if classifier_activation not in ("softmax", "sigmoid"):
+            raise ValueError("classifier_activation must be 'softmax' or 'sigmoid'")
+        self.depth, self.input_shape, self.classes = depth, tuple(input_shape), classes
+        self.head_act, self.first_strides = classifier_activation, first_strides
+        self.device = torch.device(device)
+        self.name = f"ResNetRS{depth}"
+        self.p = None
+
+    # Keras-named weights in (oracle/resnet_rs.py:weight_shapes documents the inventory)
+    def load_weights(self, W: dict):
+        d, p = self.device, {}
+        for i in range(1, 5):
+            p[f"stem{i}"] = _fold_conv_bn(W, f"stem_conv_{i}", f"stem_batch_norm_{i}", d)
+        for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
+            for bi in range(reps):
+                n = f"c{gi + 2}_block_{bi}_"
+                if bi == 0:
+                    p[n + "proj"] = _fold_conv_bn(W, n + "projection_conv", n + "projection_batch_norm", d)
+                for j in (1, 2, 3):
+                    p[n + f"conv{j}"] = _fold_conv_bn(W, n + f"conv_{j}", n + f"batch_norm_{j}", d)
+                p[n + "se1"] = _dense(W, n + "se_reduce", d)
+                p[n + "se2"] = _dense(W, n + "se_expand", d)
+        p["head_w"] = torch.from_numpy(np.asarray(W["predictions/kernel"], np.float32)).to(d).contiguous()
+        p["head_b"] = torch.from_numpy(np.asarray(W["predictions/bias"], np.float32)).to(d).contiguous()
+        self.p = p
+        return self
+
+    def _bottleneck(self, x, n, strides, use_projection):
+        p = self.p
+        shortcut = x
+        if use_projection:
+            s_in = nn.avgpool2_same(x) if strides == 2 else x
+            shortcut = nn.conv2d(s_in, *p[n + "proj"])
+        y = nn.conv2d(x, *p[n + "conv1"], act="relu")
+        y = nn.conv2d(y, *p[n + "conv2"], ksize=3, stride=strides, pad=1, act="relu")
+        y = nn.conv2d(y, *p[n + "conv3"])
+        pooled, _ = nn.global_avgpool(y)
+        hid = nn.gemm(pooled, *p[n + "se1"], act="relu")
+        gate = nn.gemm(hid, *p[n + "se2"], act="sigmoid", out_dtype=torch.float32)
+        return nn.scale_add_act(y, gate, shortcut, act="relu", out=y)
+
+    def features(self, x, taps=None):
+        """x bf16 [N,H,W,3] -> bf16 [N,h,w,2048]"""
+        p = self.p
+        if p is None:
+            raise RuntimeError("load_weights() first")
+        for i, s in ((1, self.first_strides), (2, 1), (3, 1), (4, 2)):
+            x = nn.conv2d(x, *p[f"stem{i}"], ksize=3, stride=s, pad=1, act="relu")
+        if taps is not None:
+            taps["stem"] = x
+        for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
+            for bi in range(reps):
+                x = self._bottleneck(x, f"c{gi + 2}_block_{bi}_", (1 if gi == 0 else 2) if bi == 0 else 1, bi == 0)
+            if taps is not None:
+                taps[f"c{gi + 2}"] = x
+        return x
+
+    def forward(self, x, acc=None, acc_weight=1.0, taps=None):
+        """x: bf16 (or f32) [N,H,W,3] in [0,1] on the device -> probabilities f32 [N,classes]."""
+        if x.dtype == torch.float32:
+            x = nn.cast_bf16(x)
+        f = self.features(x, taps)
+        _, feat = nn.global_avgpool(f, want_bf16=False, want_f32=True)
+        if taps is not None:
+            taps["feat"] = feat
+        return nn.head(feat, self.p["head_w"], self.p["head_b"], self.head_act == "sigmoid", acc, acc_weight)
+
+    __call__ = forward
+
+
+def ResNetRS50(**kw):
+    return ResNetRS(50, **kw)
+
+
+def ResNetRS101(**kw):
+    return ResNetRS(101, **kw)
+
+
+def ResNetRS152(**kw):
+    return ResNetRS(152, **kw)
+
+
+def ResNetRS200(**kw):
+    return ResNetRS(200, **kw)

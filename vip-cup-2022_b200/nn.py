@@ -1,0 +1,143 @@
+"""Layer-level host functions over the C ABI (include/vipcup.h).  torch tensors are only handles: every function
+passes ``data_ptr()``s and the current CUDA stream to libvipcup.so; there is no torch arithmetic on this path."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import VipError
+
+BF16 = torch.bfloat16
+ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "gelu": 2, "sigmoid": 3}
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=BF16):
+    if t is None:
+        return
+    if not t.is_cuda or not t.is_contiguous() or t.dtype != dtype:
+        raise VipError(f"{name} must be a contiguous CUDA {dtype} tensor")
+
+
+def gemm(a, w, bias=None, act=None, colscale=None, residual=None, out=None, out_dtype=BF16):
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) * colscale + residual  (tcgen05 kernel, fp32 accumulation)."""
+    _chk(a, "a"), _chk(w, "w"), _chk(residual, "residual")
+    _chk(bias, "bias", torch.float32), _chk(colscale, "colscale", torch.float32)
+    m, k = a.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise VipError(f"gemm: K mismatch {a.shape} x {w.shape}")
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    rc = _lib.lib().vip_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), m, n, k, _p(bias), ACT[act], _p(colscale),
+                                  _p(residual), 0 if residual is None else residual.stride(0), _p(out), out.stride(0),
+                                  _lib.VIP_DTYPE_BF16 if out.dtype == BF16 else _lib.VIP_DTYPE_F32, _st())
+    _lib.check(rc, "vip_gemm_bf16")
+    return out
+
+
+def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None):
+    """x bf16 [N,H,W,C]; w bf16 [Cout, Kp] with K order (r,s,c). Returns bf16 [N,Ho,Wo,Cout]."""
+    _chk(x, "x")
+    n, h, wd, c = x.shape
+    ho = (h + 2 * pad - ksize) // stride + 1
+    wo = (wd + 2 * pad - ksize) // stride + 1
+    if ksize == 1 and stride == 1 and pad == 0 and w.shape[1] == c:
+        a = x.view(n * h * wd, c)
+    else:
+        kp = w.shape[1]
+        a = torch.empty((n * ho * wo, kp), dtype=BF16, device=x.device)
+        rc = _lib.lib().vip_im2col_bf16(_p(x), n, h, wd, c, ksize, stride, pad, ho, wo, _p(a), kp, _st())
+        _lib.check(rc, "vip_im2col_bf16")
+    res2 = None if residual is None else residual.view(n * ho * wo, -1)
+    y = gemm(a, w, bias=bias, act=act, residual=res2)
+    return y.view(n, ho, wo, w.shape[0])
+
+
+def avgpool2_same(x):
+    _chk(x, "x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, c), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_avgpool2_same_bf16(_p(x), n, h, w, c, _p(out), _st()), "vip_avgpool2_same_bf16")
+    return out
+
+
+def global_avgpool(x, want_bf16=True, want_f32=False):
+    """x bf16 [N,...,C] -> ([N,C] bf16 | None, [N,C] f32 | None)"""
+    _chk(x, "x")
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    ob = torch.empty((n, c), dtype=BF16, device=x.device) if want_bf16 else None
+    of = torch.empty((n, c), dtype=torch.float32, device=x.device) if want_f32 else None
+    _lib.check(_lib.lib().vip_global_avgpool_bf16(_p(x), n, hw, c, _p(ob), _p(of), _st()), "vip_global_avgpool_bf16")
+    return ob, of
+
+
+def scale_add_act(y, gate=None, shortcut=None, act=None, out=None):
+    _chk(y, "y"), _chk(shortcut, "shortcut"), _chk(gate, "gate", torch.float32)
+    n, c = y.shape[0], y.shape[-1]
+    hw = y.numel() // (n * c)
+    if out is None:
+        out = torch.empty_like(y)
+    _lib.check(_lib.lib().vip_scale_add_act_bf16(_p(y), _p(gate), _p(shortcut), _p(out), n, hw, c, ACT[act], _st()),
+               "vip_scale_add_act_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    _chk(x, "x"), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32)
+    c = x.shape[-1]
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // c, c, eps, _st()),
+               "vip_layernorm_bf16")
+    return out
+
+
+def dwconv3x3(x, w, gelu=False):
+    _chk(x, "x"), _chk(w, "w", torch.float32)
+    n, h, wd, c = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().vip_dwconv3x3_bf16(_p(x), _p(w), _p(out), n, h, wd, c, int(gelu), _st()), "vip_dwconv3x3_bf16")
+    return out
+
+
+def maxpool3s2(x):
+    _chk(x, "x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_maxpool3s2_bf16(_p(x), _p(out), n, h, w, c, _st()), "vip_maxpool3s2_bf16")
+    return out
+
+
+def window_attention(qkv, q_global, rel_bias, B, H, W, C, ws, heads):
+    _chk(qkv, "qkv"), _chk(q_global, "q_global"), _chk(rel_bias, "rel_bias", torch.float32)
+    out = torch.empty((B * H * W, C), dtype=BF16, device=qkv.device)
+    _lib.check(_lib.lib().vip_window_attention_bf16(_p(qkv), _p(q_global), _p(rel_bias), _p(out), B, H, W, C, ws, heads,
+                                                    _st()), "vip_window_attention_bf16")
+    return out
+
+
+def head(feat_f32, w, b, sigmoid_head: bool, acc=None, acc_weight=1.0):
+    """feat f32 [N,C]; w f32 [C,k]; returns probs f32 [N,k]; optionally acc[n] += acc_weight * P(synthetic) (f64)."""
+    _chk(feat_f32, "feat", torch.float32), _chk(w, "w", torch.float32), _chk(b, "b", torch.float32)
+    _chk(acc, "acc", torch.float64)
+    n, c = feat_f32.shape
+    k = w.shape[1]
+    probs = torch.empty((n, k), dtype=torch.float32, device=feat_f32.device)
+    _lib.check(_lib.lib().vip_head_f32(_p(feat_f32), _p(w), _p(b), _p(probs), _p(acc), float(acc_weight), n, c, k,
+                                       int(sigmoid_head), _st()), "vip_head_f32")
+    return probs
+
+
+def cast_bf16(x_f32):
+    _chk(x_f32, "x", torch.float32)
+    out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
+    _lib.check(_lib.lib().vip_cast_f32_bf16(_p(x_f32), _p(out), x_f32.numel(), _st()), "vip_cast_f32_bf16")
+    return out

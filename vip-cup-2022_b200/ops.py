@@ -83,29 +83,3 @@ def selftest_div255() -> int:
     _lib.check(rc, "vip_selftest_div255")
     return int(bad.value)
 
-
-ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2, "sigmoid": 3}
-
-
-def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias=None, act=None, residual=None, out_dtype=torch.bfloat16):
-    """out[M,N] = act(a[M,K] @ b[N,K]^T + bias) + residual on the tcgen05 tensor cores (bf16 in, fp32 accumulate)."""
-    for name, t in (("a", a), ("b", b)):
-        _require_cuda(t, name)
-        if t.dtype != torch.bfloat16 or t.dim() != 2:
-            raise VipError(f"{name} must be a 2-D bfloat16 tensor")
-    m, k = a.shape
-    n = b.shape[0]
-    if b.shape[1] != k:
-        raise VipError("a and b disagree on K")
-    out = torch.empty((m, n), dtype=out_dtype, device=a.device)
-    if bias is not None:
-        _require_cuda(bias, "bias")
-    if residual is not None:
-        _require_cuda(residual, "residual")
-    with torch.cuda.device(a.device):
-        rc = _lib.lib().vip_gemm_bf16(_ptr(a), a.stride(0), _ptr(b), b.stride(0), m, n, k, _ptr(bias), ACT[act],
-                                      _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(out), n,
-                                      _lib.VIP_DTYPE_BF16 if out_dtype == torch.bfloat16 else _lib.VIP_DTYPE_F32,
-                                      _stream_ptr())
-    _lib.check(rc, "vip_gemm_bf16")
-    return out
