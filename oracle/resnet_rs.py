@@ -169,8 +169,9 @@ def random_weights(depth: int = 50, num_classes: int = 2, seed: int = 0) -> dict
         if leaf == "kernel" and len(shp) == 4:
             fan_in = shp[0] * shp[1] * shp[2]
             W[name] = (rng.standard_normal(shp) * np.sqrt(2.0 / fan_in)).astype(np.float32)
-        elif leaf == "kernel":
-            W[name] = (rng.standard_normal(shp) * (4.0 / np.sqrt(shp[0]))).astype(np.float32)
+        elif leaf == "kernel":  # Dense head: Keras default glorot-uniform
+            lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+            W[name] = rng.uniform(-lim, lim, shp).astype(np.float32)
         elif leaf == "gamma":
             W[name] = rng.uniform(0.6, 1.4, shp).astype(np.float32)
         elif leaf == "beta":
@@ -192,3 +193,22 @@ def random_weights(depth: int = 50, num_classes: int = 2, seed: int = 0) -> dict
 
 def param_count(W: dict, include_head: bool = True) -> int:
     return int(sum(v.size for k, v in W.items() if include_head or not k.startswith("predictions/")))
+
+
+def calibrate_head(W: dict, feat: np.ndarray, head_kernel: str = "predictions/kernel", head_bias: str = "predictions/bias",
+                   seed: int = 0, target_std: float = 1.5) -> dict:
+    """Random-init backbones give almost image-independent logits ('random-init degeneracy').
+    Re-draw the head so that logits are centred and spread (std ``target_std``) over the calibration features
+    ``feat`` [n, C]: probabilities then fall on both sides of the 0.487 threshold and label agreement means something.
+    Returns a copy of ``W`` with the new head."""
+    rng = np.random.default_rng(seed)
+    k = W[head_kernel].shape[1]
+    mu = feat.mean(axis=0)
+    d = rng.standard_normal((feat.shape[1], k)).astype(np.float64)
+    z = (feat - mu) @ d
+    spread = (z[:, 0] - z[:, 1]).std() if k > 1 else z[:, 0].std()
+    kern = d * (target_std / max(spread, 1e-12))
+    out = dict(W)
+    out[head_kernel] = kern.astype(np.float32)
+    out[head_bias] = (-(mu @ kern)).astype(np.float32)
+    return out

@@ -1,0 +1,56 @@
+"""End to end on the GPU box: ``main.py <input.csv> <output.csv>`` (BASELINE.json configs[0] shape: 64 synthetic 200x200
+JPEGs, ResNet-RS-50 random-init; plus GCViT-tiny as a second ensemble member) against the whole oracle pipeline
+(Pillow decode -> oracle preprocess -> oracle backbones -> oracle epilogue)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(900)
+def test_main_py_matches_oracle_pipeline(cuda_device, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_random_ckpts
+    import make_synth_dataset
+    from PIL import Image
+
+    from oracle import gcvit as G
+    from oracle import preprocess as P
+    from oracle import resnet_rs as R
+    from oracle.predict import epilogue
+    from vipcup_b200 import registry
+
+    data, models = str(tmp_path / "data"), str(tmp_path / "ckpts")
+    n = 64
+    make_synth_dataset.main(data, n)
+    make_random_ckpts.main(models, ["ResNetRS50-200x200", "GCViTTiny-224x224"])
+    out_csv = str(tmp_path / "out" / "pred.csv")
+    os.makedirs(os.path.dirname(out_csv))
+    env = dict(os.environ, VIP_MODEL_DIR=models)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), os.path.join(data, "input.csv"), out_csv],
+                       env=env, capture_output=True, text=True, timeout=800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = pd.read_csv(out_csv)
+
+    # the oracle pipeline
+    test_csv = pd.read_csv(os.path.join(data, "input.csv"))
+    imgs = [np.asarray(Image.open(os.path.join(data, f)).convert("RGB")) for f in test_csv.filename]
+    preds, margins = [], []
+    for name, dim in (("ResNetRS50-200x200", 200), ("GCViTTiny-224x224", 224)):
+        W, _ = registry.load_checkpoint(os.path.join(models, name, "ckpt", "fold0.npz"))
+        x = np.stack([P.decode_to_float(im, dim, dim) for im in imgs])
+        p = R.forward(x, W, 50) if name.startswith("ResNetRS") else G.forward(x, W, "tiny")
+        preds.append([p.astype(np.float32)])
+    ref = epilogue(test_csv, preds, tta=1, thr=0.487)
+    mean_p = np.mean([1 - p[0][:, 0] for p in preds], axis=0)
+    order = np.argsort(test_csv.filename.values)
+    decided = np.abs(mean_p[order] - 0.487) > 0.02
+    assert list(got.columns) == ["filename", "logit"] and list(got.filename) == list(ref.filename)
+    assert (got.logit.values[decided] == ref.logit.values[decided]).all()
+    print(f"labels compared: {decided.sum()}/{n}; synthetic fraction {ref.logit.mean():.2f}")

@@ -19,3 +19,23 @@ def test_resnet_rs_stage_shapes():
     assert taps["c2"].shape == (1, 50, 50, 256) and taps["c3"].shape == (1, 25, 25, 512)
     assert taps["c4"].shape == (1, 13, 13, 1024) and taps["c5"].shape == (1, 7, 7, 2048)
     assert p.shape == (1, 2) and abs(p.sum() - 1) < 1e-5
+
+
+def test_gcvit_param_counts_match_vendored_doc_table():
+    """models/keras_cv_attention_models/gcvit/__init__.py:37-43 (1000-class head): 12.0 / 28.2 / 51.1 M."""
+    from oracle import gcvit as G
+
+    for variant, millions in (("xxtiny", 12.0), ("tiny", 28.2), ("small", 51.1)):
+        n = G.param_count(G.random_weights(variant, 1000), include_unused=False)
+        assert abs(n / 1e6 - millions) < 0.06, (variant, n)
+
+
+def test_gcvit_stage_shapes():
+    from oracle import gcvit as G
+
+    x = np.random.default_rng(0).random((1, 224, 224, 3), dtype=np.float32)
+    taps = {}
+    p = G.forward(x, G.random_weights("xxtiny", 2), "xxtiny", taps=taps)
+    assert taps["stem"].shape == (1, 56, 56, 64) and taps["level0"].shape == (1, 28, 28, 128)
+    assert taps["level1"].shape == (1, 14, 14, 256) and taps["level2"].shape == (1, 7, 7, 512)
+    assert taps["level3"].shape == (1, 7, 7, 512) and p.shape == (1, 2)

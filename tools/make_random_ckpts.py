@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Writes seeded random-init checkpoints (Keras names/layouts, .npz) + ckpts.json for the synthetic runs:
+``python tools/make_random_ckpts.py <model_dir> ResNetRS50-200x200 GCViTTiny-224x224 ...``
+(checkpoints of the reference are unpublished, README.md:13; both the oracle and the CUDA path load these files)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def weights_for(model_name, num_classes, seed):
+    from oracle import gcvit as G
+    from oracle import resnet_rs as R
+
+    arch = model_name.rsplit("-", 1)[0]
+    if arch.startswith("ResNetRS"):
+        return R.random_weights(int(arch[len("ResNetRS"):]), num_classes, seed)
+    if arch.startswith("GCViT"):
+        return G.random_weights(arch[len("GCViT"):].lower(), num_classes, seed)
+    raise SystemExit(f"no random-init generator for {arch}")
+
+
+def main(model_dir, names, num_classes=2, folds=1):
+    entries = []
+    for mi, name in enumerate(names):
+        hw = [int(v) for v in name.rsplit("-", 1)[1].split("x")]
+        d = os.path.join(model_dir, name, "ckpt")
+        os.makedirs(d, exist_ok=True)
+        for f in range(folds):
+            W = weights_for(name, num_classes, seed=100 * mi + f)
+            np.savez(os.path.join(d, f"fold{f}.npz"), __num_classes__=np.int64(num_classes),
+                     __head_act__=np.array("softmax" if num_classes > 1 else "sigmoid"), **W)
+        entries.append([name, hw, 0])
+    with open(os.path.join(model_dir, "ckpts.json"), "w") as f:
+        json.dump(entries, f, indent=1)
+    print("wrote", [e[0] for e in entries], "to", model_dir)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2:])

@@ -1,0 +1,212 @@
+"""GCViT forward on the B200 kernels.  Mirrors ``models/gcvit`` of the reference (constructors gcvit.py:128-181, config
+table gcvit.py:9-42): Keras-named / Keras-layout weights in, bf16 packed GEMM operands inside.
+
+Layer -> kernel:
+  Dense qkv / proj / fc1 / fc2, Conv 1x1     tcgen05 GEMM; bias, exact GELU, layer-scale gamma and the residual add are
+                                             fused in the epilogue                                   (nn.gemm)
+  Conv 3x3 stride 2 (stem proj, reduction)   im2col view + tcgen05 GEMM                               (nn.conv2d)
+  WindowAttention (local / global query)     vip_window_attention_bf16, window partition/reverse folded into addressing
+  LayerNormalization                         vip_layernorm_bf16
+  DepthwiseConv 3x3 + GELU, SE, MaxPool      vip_dwconv3x3_bf16, vip_global_avgpool + 2 GEMMs, vip_maxpool3s2_bf16
+  head                                       vip_layernorm -> vip_global_avgpool (f32) -> vip_head_f32
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import nn
+
+CONFIGS = {  # models/gcvit/models/gcvit.py:9-42
+    "xxtiny": dict(window_size=(7, 7, 14, 7), dim=64, depths=(2, 2, 6, 2), num_heads=(2, 4, 8, 16), mlp_ratio=3.0, layer_scale=None),
+    "xtiny": dict(window_size=(7, 7, 14, 7), dim=64, depths=(3, 4, 6, 5), num_heads=(2, 4, 8, 16), mlp_ratio=3.0, layer_scale=None),
+    "tiny": dict(window_size=(7, 7, 14, 7), dim=64, depths=(3, 4, 19, 5), num_heads=(2, 4, 8, 16), mlp_ratio=3.0, layer_scale=None),
+    "small": dict(window_size=(7, 7, 14, 7), dim=96, depths=(3, 4, 19, 5), num_heads=(3, 6, 12, 24), mlp_ratio=2.0, layer_scale=1e-5),
+    "base": dict(window_size=(7, 7, 14, 7), dim=128, depths=(3, 4, 19, 5), num_heads=(4, 8, 16, 32), mlp_ratio=2.0, layer_scale=1e-5),
+}
+KEEP_DIMS = [(False, False, False), (False, False), (True,), (True,)]  # gcvit.py:70
+LN_EPS = 1e-5
+
+
+def _rel_index(ws):  # attention.py:39-50
+    coords = np.stack(np.meshgrid(np.arange(ws), np.arange(ws), indexing="ij")).reshape(2, -1)
+    rel = coords[:, :, None] - coords[:, None, :]
+    return (rel[0] + ws - 1) * (2 * ws - 1) + (rel[1] + ws - 1)
+
+
+def _pad_rows(a, mult=32):  # [N, K] -> N rounded up to `mult` with zero rows
+    n = (a.shape[0] + mult - 1) // mult * mult
+    if n == a.shape[0]:
+        return a
+    return np.concatenate([a, np.zeros((n - a.shape[0], a.shape[1]), a.dtype)], 0)
+
+
+def _pad_cols(a, mult=32):
+    k = (a.shape[1] + mult - 1) // mult * mult
+    if k == a.shape[1]:
+        return a
+    return np.concatenate([a, np.zeros((a.shape[0], k - a.shape[1]), a.dtype)], 1)
+
+
+class GCViT:
+    def __init__(self, variant="tiny", input_shape=(224, 224, 3), num_classes=2, head_act="softmax", first_strides=2,
+                 device="cuda"):
+        if variant not in CONFIGS:
+            raise ValueError(f"unknown GCViT variant {variant}")
+        if head_act not in ("softmax", "sigmoid"):
+            raise ValueError("head_act must be 'softmax' or 'sigmoid'")
+        self.cfg, self.variant = CONFIGS[variant], variant
+        self.input_shape, self.num_classes, self.head_act = tuple(input_shape), num_classes, head_act
+        self.first_strides, self.device = first_strides, torch.device(device)
+        self.name = f"GCViT{variant.capitalize()}"
+        self.p = None
+
+    # ---- weight packing ------------------------------------------------------------------------------------------
+    def _bf(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device).to(torch.bfloat16).contiguous()
+
+    def _f32(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device).contiguous()
+
+    def _dense(self, W, name, bias=True):
+        k = np.asarray(W[name + "/kernel"], np.float32)
+        k = k.reshape(-1, k.shape[-1])
+        return self._bf(k.T), (self._f32(W[name + "/bias"]) if bias else None)
+
+    def _conv3(self, W, name, bias=False):
+        k = np.asarray(W[name + "/kernel"], np.float32)  # (3,3,Cin,Cout)
+        w2 = _pad_cols(k.reshape(-1, k.shape[3]).T, 8)
+        return self._bf(w2), (self._f32(W[name + "/bias"]) if bias else None)
+
+    def _mbconv(self, W, n):
+        c = W[n + "/conv/0/depthwise_kernel"].shape[2]
+        fc0 = np.asarray(W[n + "/conv/2/fc/0/kernel"], np.float32)      # (C, C/4)
+        fc2 = np.asarray(W[n + "/conv/2/fc/2/kernel"], np.float32)      # (C/4, C)
+        return dict(dw=self._f32(np.asarray(W[n + "/conv/0/depthwise_kernel"]).reshape(3, 3, c)),
+                    fc0=self._bf(_pad_rows(fc0.T)),                      # [hid_p, C]
+                    fc2=self._bf(_pad_cols(fc2.T)),                      # [C, hid_p]
+                    pw=self._bf(np.asarray(W[n + "/conv/3/kernel"], np.float32).reshape(c, c).T))
+
+    def _reduce(self, W, n):
+        d = self._mbconv(W, n)
+        d.update(n1=(self._f32(W[n + "/norm1/gamma"]), self._f32(W[n + "/norm1/beta"])),
+                 n2=(self._f32(W[n + "/norm2/gamma"]), self._f32(W[n + "/norm2/beta"])),
+                 red=self._conv3(W, n + "/reduction")[0])
+        return d
+
+    def load_weights(self, W: dict):
+        cfg, p = self.cfg, {}
+        p["proj"] = self._conv3(W, "patch_embed/proj", bias=True)
+        p["conv_down"] = self._reduce(W, "patch_embed/conv_down")
+        for i, depth in enumerate(cfg["depths"]):
+            ws, heads = cfg["window_size"][i], cfg["num_heads"][i]
+            idx = _rel_index(ws).reshape(-1)
+            for k in range(len(KEEP_DIMS[i])):
+                p[f"q{i}_{k}"] = self._mbconv(W, f"levels/{i}/q_global_gen/to_q_global/{k}")
+            for j in range(depth):
+                n = f"levels/{i}/blocks/{j}"
+                table = np.asarray(W[n + "/attn/relative_position_bias_table"], np.float32)
+                bias = table[idx].reshape(ws * ws, ws * ws, heads).transpose(2, 0, 1)
+                p[f"b{i}_{j}"] = dict(
+                    n1=(self._f32(W[n + "/norm1/gamma"]), self._f32(W[n + "/norm1/beta"])),
+                    n2=(self._f32(W[n + "/norm2/gamma"]), self._f32(W[n + "/norm2/beta"])),
+                    qkv=self._dense(W, n + "/attn/qkv"), proj=self._dense(W, n + "/attn/proj"),
+                    fc1=self._dense(W, n + "/mlp/fc1"), fc2=self._dense(W, n + "/mlp/fc2"),
+                    rel=self._f32(bias),
+                    g1=self._f32(W[n + "/gamma1"]) if n + "/gamma1" in W else None,
+                    g2=self._f32(W[n + "/gamma2"]) if n + "/gamma2" in W else None)
+            if i < 3:
+                p[f"down{i}"] = self._reduce(W, f"levels/{i}/downsample")
+        p["norm"] = (self._f32(W["norm/gamma"]), self._f32(W["norm/beta"]))
+        p["head_w"], p["head_b"] = self._f32(W["head/kernel"]), self._f32(W["head/bias"])
+        self.p = p
+        return self
+
+    # ---- layers --------------------------------------------------------------------------------------------------
+    def _mb_apply(self, x, d):
+        """x + [pad1 -> DW3x3 -> GELU -> SE -> Conv1x1](x)   (feature.py:105-109,144-150)"""
+        b, h, w, c = x.shape
+        y = nn.dwconv3x3(x, d["dw"], gelu=True)
+        pooled, _ = nn.global_avgpool(y)
+        hid = nn.gemm(pooled, d["fc0"], act="gelu")
+        gate = nn.gemm(hid, d["fc2"], act="sigmoid", out_dtype=torch.float32)
+        y = nn.scale_add_act(y, gate, None, out=y)
+        return nn.gemm(y.view(-1, c), d["pw"], residual=x.view(-1, c)).view(b, h, w, c)
+
+    def _reduce_apply(self, x, d, stride):
+        x = nn.layernorm(x, *d["n1"], eps=LN_EPS)
+        x = self._mb_apply(x, d)
+        x = nn.conv2d(x, d["red"], None, ksize=3, stride=stride, pad=1)
+        return nn.layernorm(x, *d["n2"], eps=LN_EPS)
+
+    def _block(self, x, d, heads, ws, q_global):
+        b, h, w, c = x.shape
+        x2 = x.view(-1, c)
+        t = nn.layernorm(x2, *d["n1"], eps=LN_EPS)
+        qkv = nn.gemm(t, *d["qkv"])
+        a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
+        x2 = nn.gemm(a, *d["proj"], colscale=d["g1"], residual=x2)
+        t = nn.layernorm(x2, *d["n2"], eps=LN_EPS)
+        hdn = nn.gemm(t, *d["fc1"], act="gelu")
+        x2 = nn.gemm(hdn, *d["fc2"], colscale=d["g2"], residual=x2)
+        return x2.view(b, h, w, c)
+
+    def features(self, x, taps=None):
+        p, cfg = self.p, self.cfg
+        if p is None:
+            raise RuntimeError("load_weights() first")
+        x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
+        x = self._reduce_apply(x, p["conv_down"], self.first_strides)
+        if taps is not None:
+            taps["stem"] = x
+        for i, depth in enumerate(cfg["depths"]):
+            ws, heads = cfg["window_size"][i], cfg["num_heads"][i]
+            b, h, w, c = x.shape
+            if h % ws or w % ws:
+                raise nn.VipError(f"GCViT level {i}: feature map {h}x{w} is not a multiple of window {ws} "
+                                  "(FitWindow padding for non-224 inputs is not built)")
+            q = x
+            for k, keep in enumerate(KEEP_DIMS[i]):
+                q = self._mb_apply(q, p[f"q{i}_{k}"])
+                if not keep:
+                    q = nn.maxpool3s2(q)
+            q = q.view(b, ws * ws, c)
+            for j in range(depth):
+                x = self._block(x, p[f"b{i}_{j}"], heads, ws, q if j % 2 else None)
+            if i < 3:
+                x = self._reduce_apply(x, p[f"down{i}"], 2)
+            if taps is not None:
+                taps[f"level{i}"] = x
+        return x
+
+    def forward(self, x, acc=None, acc_weight=1.0, taps=None):
+        if x.dtype == torch.float32:
+            x = nn.cast_bf16(x)
+        f = self.features(x, taps)
+        f = nn.layernorm(f, *self.p["norm"], eps=LN_EPS)
+        _, feat = nn.global_avgpool(f, want_bf16=False, want_f32=True)
+        if taps is not None:
+            taps["feat"] = feat
+        return nn.head(feat, self.p["head_w"], self.p["head_b"], self.head_act == "sigmoid", acc, acc_weight)
+
+    __call__ = forward
+
+
+def GCViTXXTiny(**kw):
+    return GCViT("xxtiny", **kw)
+
+
+def GCViTXTiny(**kw):
+    return GCViT("xtiny", **kw)
+
+
+def GCViTTiny(**kw):
+    return GCViT("tiny", **kw)
+
+
+def GCViTSmall(**kw):
+    return GCViT("small", **kw)
+
+
+def GCViTBase(**kw):
+    return GCViT("base", **kw)

@@ -1,0 +1,76 @@
+"""Model registry of the reference: ``ckpts/ckpts.json`` entries ``[base_dir, [H, W], idx]`` with
+``base_dir = "<Arch>-<H>x<W>"`` (main.py:43-56, 186-197), mapped onto the B200 model classes.
+
+Checkpoint format: the reference loads full Keras models from ``ckpts/<base_dir>/ckpt/*.h5`` (each file = one fold,
+main.py:187-192).  HDF5 cannot be read offline (no h5py); this build reads ``*.npz`` files holding the same
+Keras-named, Keras-layout weight arrays plus optional ``__num_classes__`` / ``__head_act__`` entries
+(``tools/make_random_ckpts.py`` writes them for the synthetic runs).  ``.h5`` ingestion is listed under "next"."""
+from __future__ import annotations
+
+import os
+from glob import glob
+
+import numpy as np
+
+NAME2BS = {  # main.py:43-56
+    "convnext_large_384_in22ft1k-200x200": 16, "convnext_large_in22ft1k-200x200": 16,
+    "convnext_base_384_in22ft1k-200x200": 32, "HorNetBase-200x200": 32, "EfficientNetV2M-200x200": 64,
+    "convnext_base_in22k-200x200": 32, "ECA_NFNetL2-200x200": 32, "GCViTBase-224x224": 48, "ResNest200-200x200": 64,
+    "EfficientNetV2L-200x200": 32, "ResNetRS200-200x200": 32, "ResNet200D-200x200": 32,
+}
+
+
+def arch_of(model_name: str) -> str:
+    return model_name.rsplit("-", 1)[0]
+
+
+def constructors():
+    from .models import gcvit, resnet_rs
+
+    table = {f"ResNetRS{d}": (lambda d=d, **kw: resnet_rs.ResNetRS(d, **kw)) for d in resnet_rs.BLOCK_ARGS}
+    for v in gcvit.CONFIGS:
+        pretty = {"xxtiny": "XXTiny", "xtiny": "XTiny", "tiny": "Tiny", "small": "Small", "base": "Base"}[v]
+        table[f"GCViT{pretty}"] = (lambda v=v, **kw: gcvit.GCViT(v, **kw))
+    return table
+
+
+def supported_archs():
+    return sorted(constructors())
+
+
+def create_model(model_name, dim, num_classes=2, head_act="softmax", device="cuda"):
+    arch = arch_of(model_name)
+    table = constructors()
+    if arch not in table:
+        raise ValueError(f"no B200 implementation for architecture {arch!r} (model {model_name}); built: "
+                         f"{supported_archs()} -- the other ckpts.json backbones are listed under 'next' in DESIGN.md")
+    if arch.startswith("ResNetRS"):
+        return table[arch](input_shape=(dim[0], dim[1], 3), classes=num_classes, classifier_activation=head_act,
+                           device=device)
+    return table[arch](input_shape=(dim[0], dim[1], 3), num_classes=num_classes, head_act=head_act, device=device)
+
+
+def scan_checkpoints(model_dir, ckpt_cfg_path):
+    """main.py:186-197: returns [[paths], dim, idx] per registry entry; raises ValueError('no model found for :', ...)."""
+    import json
+
+    out = []
+    for base_dir, dim, idx in json.load(open(ckpt_cfg_path, "r")):
+        paths = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*.npz")))
+        h5 = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*h5")))
+        if paths:
+            out.append([paths, dim, idx])
+        elif h5:
+            raise ValueError(f"{base_dir}: Keras .h5 checkpoints cannot be read offline (no HDF5 reader in this build); "
+                             "convert them to .npz with Keras weight names")
+        else:
+            raise ValueError("no model found for :", base_dir)
+    return out
+
+
+def load_checkpoint(path):
+    z = np.load(path, allow_pickle=False)
+    W = {k: z[k] for k in z.files if not k.startswith("__")}
+    meta = {"num_classes": int(z["__num_classes__"]) if "__num_classes__" in z.files else None,
+            "head_act": str(z["__head_act__"]) if "__head_act__" in z.files else None}
+    return W, meta
