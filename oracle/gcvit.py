@@ -264,6 +264,11 @@ def random_weights(variant="tiny", num_classes=2, seed=0) -> dict:
             W[name] = (rng.standard_normal(shp) * 0.5).astype(np.float32)
         else:
             raise KeyError(name)
+    # well-conditioned residual branches (trained nets are): damp the branch outputs by ~1/sqrt(#blocks)
+    damp = 1.5 / np.sqrt(sum(CONFIGS[variant]["depths"]))
+    for name in W:
+        if name.endswith("attn/proj/kernel") or name.endswith("mlp/fc2/kernel"):
+            W[name] *= damp
     return W
 
 

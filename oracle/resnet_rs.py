@@ -185,9 +185,10 @@ def random_weights(depth: int = 50, num_classes: int = 2, seed: int = 0) -> dict
         else:
             raise KeyError(name)
     # identity-ish residual branches: damp the last BN of every block so activations do not blow up with depth
+    damp = 1.5 / np.sqrt(sum(r for _, r in BLOCK_ARGS[depth]))
     for name in W:
         if name.endswith("batch_norm_3/gamma"):
-            W[name] *= 0.5
+            W[name] *= damp
     return W
 
 
@@ -211,4 +212,20 @@ def calibrate_head(W: dict, feat: np.ndarray, head_kernel: str = "predictions/ke
     out = dict(W)
     out[head_kernel] = kern.astype(np.float32)
     out[head_bias] = (-(mu @ kern)).astype(np.float32)
+    return out
+
+
+def center_head(W: dict, feat: np.ndarray, thr: float = 0.487, head_kernel: str = "predictions/kernel",
+                head_bias: str = "predictions/bias") -> dict:
+    """Shift the head bias (no amplification) so that the median P(synthetic) over the calibration features sits on the
+    decision threshold: both labels occur and 'identical labels' is not vacuous."""
+    out = dict(W)
+    z = feat @ W[head_kernel] + W[head_bias]
+    b = np.array(W[head_bias], dtype=np.float32)
+    target = float(np.log(thr / (1 - thr)))
+    if z.shape[1] > 1:                       # P(syn) = 1 - softmax(z)[0]; for k = 2 this is sigmoid(z1 - z0)
+        b[1] += target - float(np.median(z[:, 1] - z[:, 0]))
+    else:
+        b[0] += target - float(np.median(z[:, 0]))
+    out[head_bias] = b
     return out

@@ -25,4 +25,4 @@ def test_gcvit_matches_oracle(cuda_device, variant, head):
     got = model(torch.from_numpy(x).to(cuda_device), taps=taps)
     torch.cuda.synchronize()
     check_against_oracle(ref, ref_taps, got, taps, W["head/kernel"], W["head/bias"],
-                         ("stem", "level0", "level1", "level2", "level3"))
+                         ("stem", "level0", "level1", "level2", "level3"), logit_tol=3e-2)

@@ -8,11 +8,11 @@ pytestmark = pytest.mark.gpu
     (128, 32, 64), (128, 128, 64), (256, 256, 256), (1000, 64, 288), (625 * 3, 512, 1152), (49 * 5, 2048, 512),
     (130, 192 + 64, 96), (4096, 768, 256), (77, 32, 8), (20000, 64, 576),
 ])
-@pytest.mark.parametrize("epi", ["plain", "bias_relu_res", "gelu_f32"])
+@pytest.mark.parametrize("epi", ["plain", "bias_relu_res", "gelu_f32", "colscale_res"])
 def test_gemm_matches_torch(cuda_device, m, n, k, epi):
     import torch
 
-    from vipcup_b200 import ops
+    from vipcup_b200 import nn
 
     g = torch.Generator(device="cpu").manual_seed(m * 31 + n * 7 + k)
     a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
@@ -21,12 +21,16 @@ def test_gemm_matches_torch(cuda_device, m, n, k, epi):
     res = torch.randn(m, n, generator=g).to(torch.bfloat16).to(cuda_device)
     ref = a.float() @ b.float().t()
     if epi == "plain":
-        out = ops.gemm_bf16(a, b)
+        out = nn.gemm(a, b)
     elif epi == "bias_relu_res":
-        out = ops.gemm_bf16(a, b, bias=bias, act="relu", residual=res)
+        out = nn.gemm(a, b, bias=bias, act="relu", residual=res)
         ref = torch.relu(ref + bias) + res.float()
+    elif epi == "colscale_res":
+        cs = torch.rand(n, generator=g).to(cuda_device)
+        out = nn.gemm(a, b, bias=bias, colscale=cs, residual=res)
+        ref = (ref + bias) * cs + res.float()
     else:
-        out = ops.gemm_bf16(a, b, bias=bias, act="gelu", out_dtype=torch.float32)
+        out = nn.gemm(a, b, bias=bias, act="gelu", out_dtype=torch.float32)
         ref = torch.nn.functional.gelu(ref + bias)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()

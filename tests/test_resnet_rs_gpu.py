@@ -1,10 +1,11 @@
 """ResNet-RS forward on the B200 kernels versus the fp32 PyTorch-CPU oracle on the same random-init weights.
 
 Tolerances written here (see DESIGN.md "numerics"): the bf16 path quantises every GEMM operand to 8 mantissa bits; on
-these random-init networks that gives an rms feature error of about 1 % of the activation scale and a max logit error
-of about 2e-2 (measured on B200, tools/diag_models.py), i.e. 2x the 1e-2 figure BASELINE.json hopes for bf16.
-Asserted: feature maps within 5 % of their max, logits within 3e-2, probabilities within 1.5e-2, identical labels for
-every image whose oracle probability is further than 0.02 from the 0.487 threshold (main.py:225)."""
+these random-init networks that gives an rms feature error of about 0.5-1 % of the activation scale.  Measured max logit
+error on B200 (tests/tools/diag_models.py): ResNet-RS-50 7e-3, RS-101 9e-3, GCViT-xxtiny 6e-3, GCViT-small 6e-3..1.4e-2,
+GCViT-tiny 2.1e-2 -- i.e. the 1e-2 figure of BASELINE.json holds for ResNet-RS and is missed by 2x on GCViT-tiny.
+Asserted: feature maps within 5 % of their max, logits within 1e-2 (ResNet-RS) / 3e-2 (GCViT), probabilities within
+1.5e-2, identical labels for every image whose oracle probability is further than 0.02 from the 0.487 threshold."""
 import numpy as np
 import pytest
 
@@ -19,7 +20,7 @@ def _inputs(n, hw=200):
     return np.stack([P.decode_to_float(P.synth_image(i), hw, hw) for i in range(n)])
 
 
-def check_against_oracle(ref, ref_taps, got, taps, Wk, Wb, stages):
+def check_against_oracle(ref, ref_taps, got, taps, Wk, Wb, stages, logit_tol=1e-2):
     for name in stages:
         a, b = taps[name].float().cpu().numpy(), ref_taps[name]
         assert a.shape == b.shape, name
@@ -36,7 +37,7 @@ def check_against_oracle(ref, ref_taps, got, taps, Wk, Wb, stages):
     decided = np.abs(p_ref - THR) > 0.02
     agree = ((p_ref > THR) == (p_got > THR))[decided].all()
     print(f"max logit err {logit_err:.3e}  max prob err {prob_err:.3e}  labels compared {decided.sum()}/{len(decided)}")
-    assert logit_err <= 3e-2 and prob_err <= 1.5e-2 and agree
+    assert logit_err <= logit_tol and prob_err <= 1.5e-2 and agree
 
 
 @pytest.mark.parametrize("depth,head", [(50, "softmax"), (50, "sigmoid"), (101, "softmax")])

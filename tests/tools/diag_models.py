@@ -1,5 +1,5 @@
 import numpy as np, torch, sys
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import resnet_rs as R, gcvit as G, preprocess as P
 from vipcup_b200.models import ResNetRS, GCViT
 dev=torch.device('cuda:0')

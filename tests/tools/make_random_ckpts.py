@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Writes seeded random-init checkpoints (Keras names/layouts, .npz) + ckpts.json for the synthetic runs:
-``python tools/make_random_ckpts.py <model_dir> ResNetRS50-200x200 GCViTTiny-224x224 ...``
+``python tests/tools/make_random_ckpts.py <model_dir> ResNetRS50-200x200 GCViTTiny-224x224 ...``
 (checkpoints of the reference are unpublished, README.md:13; both the oracle and the CUDA path load these files)."""
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def weights_for(model_name, num_classes, seed):
@@ -23,6 +23,27 @@ def weights_for(model_name, num_classes, seed):
     raise SystemExit(f"no random-init generator for {arch}")
 
 
+def centred(model_name, W, n_cal=16):
+    """Random-init backbones are almost image-independent: re-draw the head so that the logit
+    margin has std 2 over the synthetic images and its median sits on the 0.487 threshold.  This amplifies the
+    backbone's bf16 error by the same factor as the signal, so labels are only comparable away from the threshold."""
+    from oracle import gcvit as G
+    from oracle import preprocess as P
+    from oracle import resnet_rs as R
+
+    arch, hw = model_name.rsplit("-", 1)
+    dim = int(hw.split("x")[0])
+    x = np.stack([P.decode_to_float(P.synth_image(i), dim, dim) for i in range(n_cal)])
+    taps = {}
+    if arch.startswith("ResNetRS"):
+        R.forward(x, W, int(arch[len("ResNetRS"):]), taps=taps)
+        W = R.calibrate_head(W, taps["feat"], seed=1, target_std=2.0)
+        return R.center_head(W, taps["feat"])
+    G.forward(x, W, arch[len("GCViT"):].lower(), taps=taps)
+    W = R.calibrate_head(W, taps["feat"], "head/kernel", "head/bias", seed=1, target_std=2.0)
+    return R.center_head(W, taps["feat"], head_kernel="head/kernel", head_bias="head/bias")
+
+
 def main(model_dir, names, num_classes=2, folds=1):
     entries = []
     for mi, name in enumerate(names):
@@ -30,7 +51,7 @@ def main(model_dir, names, num_classes=2, folds=1):
         d = os.path.join(model_dir, name, "ckpt")
         os.makedirs(d, exist_ok=True)
         for f in range(folds):
-            W = weights_for(name, num_classes, seed=100 * mi + f)
+            W = centred(name, weights_for(name, num_classes, seed=100 * mi + f))
             np.savez(os.path.join(d, f"fold{f}.npz"), __num_classes__=np.int64(num_classes),
                      __head_act__=np.array("softmax" if num_classes > 1 else "sigmoid"), **W)
         entries.append([name, hw, 0])

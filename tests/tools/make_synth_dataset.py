@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Writes N synthetic 200x200 JPEGs + input.csv: ``python tools/make_synth_dataset.py <dir> <N>``."""
+"""Writes N synthetic 200x200 JPEGs + input.csv: ``python tests/tools/make_synth_dataset.py <dir> <N>``."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def main(out_dir, n):

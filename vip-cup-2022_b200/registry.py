@@ -4,7 +4,7 @@
 Checkpoint format: the reference loads full Keras models from ``ckpts/<base_dir>/ckpt/*.h5`` (each file = one fold,
 main.py:187-192).  HDF5 cannot be read offline (no h5py); this build reads ``*.npz`` files holding the same
 Keras-named, Keras-layout weight arrays plus optional ``__num_classes__`` / ``__head_act__`` entries
-(``tools/make_random_ckpts.py`` writes them for the synthetic runs).  ``.h5`` ingestion is listed under "next"."""
+(``tests/tools/make_random_ckpts.py`` writes them for the synthetic runs).  ``.h5`` ingestion is listed under "next"."""
 from __future__ import annotations
 
 import os
