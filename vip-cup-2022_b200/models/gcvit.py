@@ -94,6 +94,69 @@ class GCViT:
                  red=self._conv3(W, n + "/reduction")[0])
         return d
 
+    def weight_shapes(self) -> dict:
+        """Keras weight inventory (name -> shape): embedding.py:15, feature.py:20-22,57-59,87-101,128-139,
+        attention.py:24-33, block.py:28-56, gcvit.py:79,88."""
+        cfg, s = self.cfg, {}
+
+        def lnorm(n, c):
+            s[n + "/gamma"], s[n + "/beta"] = (c,), (c,)
+
+        def mb(n, c):
+            s[n + "/conv/0/depthwise_kernel"] = (3, 3, c, 1)
+            s[n + "/conv/2/fc/0/kernel"], s[n + "/conv/2/fc/2/kernel"] = (c, int(c * 0.25)), (int(c * 0.25), c)
+            s[n + "/conv/3/kernel"] = (1, 1, c, c)
+
+        def reduce(n, c, keep):
+            lnorm(n + "/norm1", c)
+            mb(n, c)
+            s[n + "/reduction/kernel"] = (3, 3, c, c if keep else 2 * c)
+            lnorm(n + "/norm2", c if keep else 2 * c)
+
+        c = cfg["dim"]
+        s["patch_embed/proj/kernel"], s["patch_embed/proj/bias"] = (3, 3, 3, c), (c,)
+        reduce("patch_embed/conv_down", c, True)
+        for i, depth in enumerate(cfg["depths"]):
+            ws, heads, hidden = cfg["window_size"][i], cfg["num_heads"][i], int(c * cfg["mlp_ratio"])
+            for k in range(len(KEEP_DIMS[i])):
+                mb(f"levels/{i}/q_global_gen/to_q_global/{k}", c)
+            for j in range(depth):
+                n, nq = f"levels/{i}/blocks/{j}", (2 if j % 2 else 3)
+                lnorm(n + "/norm1", c)
+                lnorm(n + "/norm2", c)
+                s[n + "/attn/qkv/kernel"], s[n + "/attn/qkv/bias"] = (c, nq * c), (nq * c,)
+                s[n + "/attn/relative_position_bias_table"] = ((2 * ws - 1) ** 2, heads)
+                s[n + "/attn/proj/kernel"], s[n + "/attn/proj/bias"] = (c, c), (c,)
+                s[n + "/mlp/fc1/kernel"], s[n + "/mlp/fc1/bias"] = (c, hidden), (hidden,)
+                s[n + "/mlp/fc2/kernel"], s[n + "/mlp/fc2/bias"] = (hidden, c), (c,)
+                if cfg["layer_scale"] is not None:
+                    s[n + "/gamma1"], s[n + "/gamma2"] = (c,), (c,)
+            if i < 3:
+                reduce(f"levels/{i}/downsample", c, False)
+                c *= 2
+        lnorm("norm", c)
+        s["head/kernel"], s["head/bias"] = (c, self.num_classes), (self.num_classes,)
+        return s
+
+    def init_random(self, seed=0):
+        """Random initialisation like the Keras constructor (glorot-scale kernels, unit LayerNorm, zero biases)."""
+        rng = np.random.default_rng(seed)
+        W = {}
+        for name, shp in self.weight_shapes().items():
+            leaf = name.rsplit("/", 1)[1]
+            if leaf in ("kernel", "depthwise_kernel"):
+                fan_in = int(np.prod(shp[:-1])) if leaf == "kernel" else 9
+                W[name] = (rng.standard_normal(shp) * np.sqrt(1.0 / fan_in)).astype(np.float32)
+            elif leaf == "gamma":
+                W[name] = np.ones(shp, np.float32)
+            elif leaf in ("gamma1", "gamma2"):
+                W[name] = np.full(shp, 0.1, np.float32)
+            elif leaf == "relative_position_bias_table":
+                W[name] = (rng.standard_normal(shp) * 0.02).astype(np.float32)
+            else:
+                W[name] = np.zeros(shp, np.float32)
+        return self.load_weights(W)
+
     def load_weights(self, W: dict):
         cfg, p = self.cfg, {}
         p["proj"] = self._conv3(W, "patch_embed/proj", bias=True)

@@ -62,7 +62,48 @@ class ResNetRS:
         self.name = f"ResNetRS{depth}"
         self.p = None
 
-    # Keras-named weights in (oracle/resnet_rs.py:weight_shapes documents the inventory)
+    def weight_shapes(self) -> dict:
+        """Keras weight inventory (name -> shape) of this architecture (resnet_rs_model.py:64-183, 468-476)."""
+        s = {}
+
+        def bnorm(n, c):
+            for q in ("gamma", "beta", "moving_mean", "moving_variance"):
+                s[f"{n}/{q}"] = (c,)
+
+        for i, (ci, co) in enumerate(((3, 32), (32, 32), (32, 64), (64, 64)), 1):
+            s[f"stem_conv_{i}/kernel"] = (3, 3, ci, co)
+            bnorm(f"stem_batch_norm_{i}", co)
+        cin = 64
+        for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
+            for bi in range(reps):
+                n = f"c{gi + 2}_block_{bi}_"
+                if bi == 0:
+                    s[n + "projection_conv/kernel"] = (1, 1, cin, 4 * f)
+                    bnorm(n + "projection_batch_norm", 4 * f)
+                for j, (kk, a, b) in enumerate(((1, cin, f), (3, f, f), (1, f, 4 * f)), 1):
+                    s[n + f"conv_{j}/kernel"] = (kk, kk, a, b)
+                    bnorm(n + f"batch_norm_{j}", b)
+                s[n + "se_reduce/kernel"], s[n + "se_reduce/bias"] = (1, 1, 4 * f, f), (f,)
+                s[n + "se_expand/kernel"], s[n + "se_expand/bias"] = (1, 1, f, 4 * f), (4 * f,)
+                cin = 4 * f
+        s["predictions/kernel"], s["predictions/bias"] = (cin, self.classes), (self.classes,)
+        return s
+
+    def init_random(self, seed=0):
+        """``weights=None`` of the Keras constructor: fan-in scaled normal kernels, identity BatchNorm, zero biases."""
+        rng = np.random.default_rng(seed)
+        W = {}
+        for name, shp in self.weight_shapes().items():
+            leaf = name.rsplit("/", 1)[1]
+            if leaf == "kernel":
+                W[name] = (rng.standard_normal(shp) * np.sqrt(2.0 / np.prod(shp[:-1]))).astype(np.float32)
+            elif leaf in ("gamma", "moving_variance"):
+                W[name] = np.ones(shp, np.float32) * (0.3 if name.endswith("batch_norm_3/gamma") else 1.0)
+            else:
+                W[name] = np.zeros(shp, np.float32)
+        return self.load_weights(W)
+
+    # Keras-named weights in (SURVEY.md B.4)
     def load_weights(self, W: dict):
         d, p = self.device, {}
         for i in range(1, 5):
