@@ -110,9 +110,10 @@ int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, i
 /* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
 int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
 /* Window attention, head_dim 32, window partition/reverse folded into addressing: gcvit attention.py:52-83, window.py:3-14.
- * qkv bf16 [B*H*W, 3C] (local) or [B*H*W, 2C] = k,v (global, q_global bf16 [B, ws*ws, C] != NULL); rel_bias f32
- * [heads, ws*ws, ws*ws] (table gathered by relative_position_index); out bf16 [B*H*W, C]. */
-int vip_window_attention_bf16(const void* qkv, const void* q_global, const float* rel_bias, void* out, int B, int H, int W,
+ * qkv bf16 [B*H*W, 3C] (local) or [B*H*W, 2C] = k,v (global, q_global bf16 [B, ws*ws, C] != NULL); rel_table f32
+ * [heads, (2ws-1)^2] = relative_position_bias_table transposed, gathered inside the kernel with the index of
+ * attention.py:39-50; out bf16 [B*H*W, C].  ws 7 and 14 are built. */
+int vip_window_attention_bf16(const void* qkv, const void* q_global, const float* rel_table, void* out, int B, int H, int W,
                               int C, int ws, int heads, void* cuda_stream);
 /* Classifier head on pooled f32 features [N,C]: Dense(k) (w f32 [C,k], b [k]) + softmax (sigmoid_head = 0) or sigmoid,
  * probs f32 [N,k]; when acc != NULL also acc[n] += acc_weight * P(synthetic) with P = k > 1 ? 1 - probs[n,0] : probs[n,0]

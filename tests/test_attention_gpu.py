@@ -1,0 +1,55 @@
+"""vip_window_attention_bf16 (tensor-core window attention, models/gcvit/layers/attention.py:52-83 with
+window_partition/reverse of layers/window.py:3-14 folded in) against a plain PyTorch fp32 restatement of the same op on
+the same bf16-rounded inputs.  Tolerance: bf16 output rounding + bf16 P operand -> 2e-2 absolute on O(1) values."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_index(ws):  # attention.py:39-50
+    coords = np.stack(np.meshgrid(np.arange(ws), np.arange(ws), indexing="ij")).reshape(2, -1)
+    rel = coords[:, :, None] - coords[:, None, :]
+    return (rel[0] + ws - 1) * (2 * ws - 1) + (rel[1] + ws - 1)
+
+
+def _ref(qkv, qg, table, B, H, W, C, ws, heads):
+    import torch
+
+    N, hd = ws * ws, 32
+    parts = qkv.shape[-1] // C
+    x = qkv.float().view(B, H // ws, ws, W // ws, ws, parts * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, N, parts, heads, hd)
+    x = x.permute(2, 0, 3, 1, 4)                       # [parts, B_, heads, N, hd]
+    if qg is None:
+        q, k, v = x[0], x[1], x[2]
+    else:
+        k, v = x[0], x[1]
+        nw = k.shape[0] // B
+        q = qg.float().view(B, 1, N, heads, hd).expand(B, nw, N, heads, hd).reshape(-1, N, heads, hd).permute(0, 2, 1, 3)
+    attn = (q * hd ** -0.5) @ k.transpose(-1, -2)
+    bias = table.float()[:, torch.from_numpy(_rel_index(ws).reshape(-1)).to(table.device)].view(heads, N, N)
+    attn = torch.softmax(attn + bias[None], -1)
+    o = (attn @ v).permute(0, 2, 1, 3).reshape(-1, N, C)          # [B_, N, C]
+    o = o.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B * H * W, C)
+    return o
+
+
+@pytest.mark.parametrize("B,H,ws,heads,glob", [(2, 14, 7, 2, False), (3, 21, 7, 4, True), (2, 14, 14, 8, False),
+                                               (1, 14, 14, 3, True), (5, 7, 7, 16, False), (1, 56, 7, 2, True)])
+def test_window_attention_matches_torch(cuda_device, B, H, ws, heads, glob):
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + H + heads)
+    C, W, N = heads * 32, H, ws * ws
+    parts = 2 if glob else 3
+    qkv = (torch.randn((B * H * W, parts * C), generator=g) * 1.5).to(torch.bfloat16).to(cuda_device)
+    qg = (torch.randn((B, N, C), generator=g) * 1.5).to(torch.bfloat16).to(cuda_device) if glob else None
+    table = (torch.randn((heads, (2 * ws - 1) ** 2), generator=g) * 0.5).to(cuda_device)
+    got = nn.window_attention(qkv, qg, table, B, H, W, C, ws, heads).float()
+    ref = _ref(qkv, qg, table, B, H, W, C, ws, heads)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    assert torch.isfinite(got).all()
+    assert err < 2e-2, f"max abs err {err}"

@@ -163,19 +163,18 @@ class GCViT:
         p["conv_down"] = self._reduce(W, "patch_embed/conv_down")
         for i, depth in enumerate(cfg["depths"]):
             ws, heads = cfg["window_size"][i], cfg["num_heads"][i]
-            idx = _rel_index(ws).reshape(-1)
             for k in range(len(KEEP_DIMS[i])):
                 p[f"q{i}_{k}"] = self._mbconv(W, f"levels/{i}/q_global_gen/to_q_global/{k}")
             for j in range(depth):
                 n = f"levels/{i}/blocks/{j}"
-                table = np.asarray(W[n + "/attn/relative_position_bias_table"], np.float32)
-                bias = table[idx].reshape(ws * ws, ws * ws, heads).transpose(2, 0, 1)
+                # [(2ws-1)^2, heads] -> [heads, (2ws-1)^2]; the kernel gathers by relative position (attention.py:39-50)
+                table = np.asarray(W[n + "/attn/relative_position_bias_table"], np.float32).T
                 p[f"b{i}_{j}"] = dict(
                     n1=(self._f32(W[n + "/norm1/gamma"]), self._f32(W[n + "/norm1/beta"])),
                     n2=(self._f32(W[n + "/norm2/gamma"]), self._f32(W[n + "/norm2/beta"])),
                     qkv=self._dense(W, n + "/attn/qkv"), proj=self._dense(W, n + "/attn/proj"),
                     fc1=self._dense(W, n + "/mlp/fc1"), fc2=self._dense(W, n + "/mlp/fc2"),
-                    rel=self._f32(bias),
+                    rel=self._f32(table),
                     g1=self._f32(W[n + "/gamma1"]) if n + "/gamma1" in W else None,
                     g2=self._f32(W[n + "/gamma2"]) if n + "/gamma2" in W else None)
             if i < 3:
