@@ -84,10 +84,50 @@ int vip_preprocess_host(const uint8_t* src, int N, int Hs, int Ws, const int32_t
  *   out[M,N] = act(A[M,K] x B[N,K]^T + bias[N]) * colscale[N] + residual[M,N]
  * A, B, residual: device bf16, row-major (lda / ldb / ldr elements between rows, multiples of 8); bias, colscale
  * (GCViT layer-scale gamma, models/gcvit/layers/block.py:41-56,79-80): device f32 or NULL; act: 0 none, 1 relu,
- * 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).  K % 8 == 0, N % 32 == 0. */
+ * 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).  K % 8 == 0, N % 8 == 0. */
 int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
                   const float* colscale, const void* residual, int ldr, void* out, int ldc, int out_dtype,
                   void* cuda_stream);
+
+/* Epilogue description of vip_gemm_bf16_ex / vip_conv2d_bf16, applied per output element (m, n) in this order:
+ *   v = acc
+ *   v = rstd[m] * (v - mean[m] * ln_colsum[n])   if ln_stats: LayerNormalization of the A rows folded into the contraction
+ *        (models/gcvit/layers/block.py:28,39 feeding attention.py:25 / feature.py:20): (mean, rstd) come from ln_stats[m] =
+ *        (sum, sum of squares) over ln_cols columns; B must hold gamma-scaled weights, bias must hold beta @ W + b
+ *   v += bias[n];  v = act(v);  v *= colscale[n];  v += residual[m, n];  store as bf16 or f32
+ *   row_stats[m] += (sum_n out, sum_n out^2)      if row_stats: feeds the ln_stats of the next contraction (f32 atomics)
+ *   gap[m / gap_rows, n] += out                   if gap: GlobalAveragePooling2D partial sums (SE squeeze,
+ *        models/resnet_rs/resnet_rs_model.py:149) (f32 atomics)
+ * row_stats and gap are accumulated: the caller zeroes them (vip_memset_async). */
+typedef struct vip_epilogue {
+  const float* bias;      /* [N] or NULL */
+  int act;                /* 0 none, 1 relu, 2 gelu (erf), 3 sigmoid */
+  const float* colscale;  /* [N] or NULL */
+  const void* residual;   /* bf16 [M, ldr] or NULL */
+  int ldr;
+  void* out;              /* bf16 or f32 [M, ldc] */
+  int ldc;
+  int out_dtype;          /* VIP_DTYPE_* */
+  const float* ln_stats;  /* [M, 2] or NULL */
+  const float* ln_colsum; /* [N] */
+  int ln_cols;
+  float ln_eps;
+  float* row_stats;       /* [M, 2] or NULL */
+  float* gap;             /* [ceil(M / gap_rows), N] or NULL */
+  int gap_rows;
+} vip_epilogue_t;
+
+/* vip_gemm_bf16 with the full epilogue. N, K, lda, ldb, ldc, ldr multiples of 8. */
+int vip_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const vip_epilogue_t* epi,
+                     void* cuda_stream);
+/* Conv2D with explicit symmetric zero padding as an implicit GEMM (no im2col matrix in memory): x bf16 [N,H,W,C] NHWC,
+ * w bf16 [Cout, ksize*ksize*C] (K order r,s,c = Keras kernel (kh,kw,Cin,Cout) flattened, ldw elements between rows),
+ * output rows = N*Ho*Wo pixels with Ho = (H + 2 pad - ksize) / stride + 1.  C, Cout % 8 == 0.
+ * models/resnet_rs/resnet_rs_model.py:64-84, model_utils.py:22-46; gcvit layers/feature.py:97-98. */
+int vip_conv2d_bf16(const void* x, int N, int H, int W, int C, const void* w, int ldw, int Cout, int ksize, int stride,
+                    int pad, const vip_epilogue_t* epi, void* cuda_stream);
+/* cudaMemsetAsync on the caller's stream (zeroing of row_stats / gap accumulators). */
+int vip_memset_async(void* ptr, int value, size_t bytes, void* cuda_stream);
 
 /* ---- layer kernels of the backbones; activations are device bf16 NHWC / [tokens, C], C % 8 == 0 ------------------ */
 /* Conv2D with explicit zero padding as an im2col matrix [N*Ho*Wo, Kp] (K order r,s,c = Keras kernel (kh,kw,Cin,Cout)
@@ -102,9 +142,11 @@ int vip_global_avgpool_bf16(const void* x, int N, int HW, int C, void* out_bf16,
  * SE excite + Add + ReLU, resnet_rs_model.py:183,278-280; gcvit feature.py:66,109,150 */
 int vip_scale_add_act_bf16(const void* y, const float* gate, const void* shortcut, void* out, int N, int HW, int C, int act,
                            void* cuda_stream);
-/* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79 */
-int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, long long M, int C, float eps,
-                       void* cuda_stream);
+/* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79.  row_stats
+ * (f32 [M,2] or NULL) receives (sum, sum of squares) of every OUTPUT row, the ln_stats of a LayerNorm folded into the
+ * next contraction. */
+int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats, long long M,
+                       int C, float eps, void* cuda_stream);
 /* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ exact GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134 */
 int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, int W, int C, int gelu, void* cuda_stream);
 /* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
@@ -121,6 +163,8 @@ int vip_window_attention_bf16(const void* qkv, const void* q_global, const float
 int vip_head_f32(const float* feat, const float* w, const float* b, float* probs, double* acc, double acc_weight, int N,
                  int C, int k, int sigmoid_head, void* cuda_stream);
 int vip_cast_f32_bf16(const float* x, void* out, long long n, void* cuda_stream);
+/* out = bf16(x * scale): pooled sums of the fused gap epilogue -> means (SE squeeze, resnet_rs_model.py:149) */
+int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* cuda_stream);
 
 /* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
  * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */

@@ -36,3 +36,53 @@ def test_gemm_matches_torch(cuda_device, m, n, k, epi):
     err = (out.float() - ref).abs().max().item()
     tol = 2e-2 * max(1.0, ref.abs().max().item()) if out.dtype == torch.bfloat16 else 1e-3 * max(1.0, k ** 0.5)
     assert err <= tol, f"max abs err {err} > {tol}"
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 64, 64), (5000, 256, 128), (1000, 384, 96), (777, 768, 256)])
+def test_gemm_folded_layernorm_and_row_stats(cuda_device, m, n, k):
+    """LayerNorm folded into the contraction (ln_stats / ln_colsum) and the row statistics a producer GEMM emits for it."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(m + n + k)
+    # producer: x = a0 @ w0^T (bf16) with fused row statistics
+    a0 = (torch.randn(m, 64, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w0 = (torch.randn(k, 64, generator=g) * 0.3).to(torch.bfloat16).to(cuda_device)
+    b0 = (torch.randn(k, generator=g) * 2.0).to(cuda_device)          # DC offset: mean removal must really happen
+    stats = nn.zero_(torch.empty((m, 2), dtype=torch.float32, device=cuda_device))
+    x = nn.gemm(a0, w0, bias=b0, row_stats=stats)
+    xs = x.float()
+    torch.cuda.synchronize()
+    assert torch.allclose(stats[:, 0], xs.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+    # consumer: LN(x) * gamma + beta, then @ W + b, as one contraction on the raw x
+    gamma = (1.0 + 0.2 * torch.randn(k, generator=g)).to(cuda_device)
+    beta = (0.3 * torch.randn(k, generator=g)).to(cuda_device)
+    wt = (torch.randn(n, k, generator=g) * 0.2).to(cuda_device)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    wg = (wt * gamma[None, :]).to(torch.bfloat16)
+    colsum = wg.float().sum(1).contiguous()
+    b2 = (wt @ beta + bias).contiguous()
+    out = nn.gemm(x, wg, bias=b2, act="gelu", ln_stats=stats, ln_colsum=colsum, ln_cols=k, ln_eps=1e-5)
+    ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xs, (k,), gamma, beta, 1e-5) @ wt.t() + bias)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 3e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("nimg,hw,n,k", [(3, 49, 256, 64), (5, 169, 512, 128), (2, 2500, 64, 64), (7, 100, 2048, 512)])
+def test_gemm_fused_global_average_pool(cuda_device, nimg, hw, n, k):
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(nimg * hw + n)
+    a = (torch.randn(nimg * hw, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    gap = nn.zero_(torch.empty((nimg, n), dtype=torch.float32, device=cuda_device))
+    out = nn.gemm(a, b, gap=gap, gap_rows=hw)
+    torch.cuda.synchronize()
+    ref = out.float().view(nimg, hw, n).sum(1)
+    assert torch.allclose(gap, ref, rtol=1e-3, atol=1e-2 * hw ** 0.5), (gap - ref).abs().max().item()
+    assert (out.float() - a.float() @ b.float().t()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())

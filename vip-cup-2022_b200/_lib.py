@@ -15,6 +15,14 @@ class VipError(RuntimeError):
     pass
 
 
+class Epilogue(C.Structure):
+    """vip_epilogue_t of include/vipcup.h"""
+    _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("colscale", C.c_void_p), ("residual", C.c_void_p),
+                ("ldr", C.c_int), ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
+                ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
+                ("row_stats", C.c_void_p), ("gap", C.c_void_p), ("gap_rows", C.c_int)]
+
+
 _lib = None
 
 # name -> (restype, argtypes); must list every symbol include/vipcup.h declares (tests check this)
@@ -29,18 +37,24 @@ SIGNATURES = {
                                       C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "vip_gemm_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vip_gemm_bf16_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(Epilogue), C.c_void_p]),
+    "vip_conv2d_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.POINTER(Epilogue), C.c_void_p]),
+    "vip_memset_async": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
     "vip_im2col_bf16": (C.c_int, [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p, C.c_int, C.c_void_p]),
     "vip_avgpool2_same_bf16": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]),
     "vip_global_avgpool_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vip_scale_add_act_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p]),
-    "vip_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float,
-                                     C.c_void_p]),
+    "vip_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                     C.c_float, C.c_void_p]),
     "vip_dwconv3x3_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "vip_maxpool3s2_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "vip_window_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "vip_head_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
+    "vip_scale_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vip_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vip_selftest_div255": (C.c_int, [C.POINTER(C.c_uint64), C.c_void_p]),
 }

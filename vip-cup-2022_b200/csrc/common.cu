@@ -32,4 +32,11 @@ const char* vip_last_error(void) { return vip::g_err; }
 int64_t vip_launch_count(void) { return vip::g_launches; }
 void vip_launch_count_reset(void) { vip::g_launches = 0; }
 
+int vip_memset_async(void* ptr, int value, size_t bytes, void* cuda_stream) {
+  VIP_REQUIRE(ptr != nullptr || bytes == 0, VIP_ERR_INVALID, "vip_memset_async: null pointer");
+  if (bytes == 0) return VIP_OK;
+  VIP_CUDA(cudaMemsetAsync(ptr, value, bytes, reinterpret_cast<cudaStream_t>(cuda_stream)));
+  return VIP_OK;
+}
+
 }  // extern "C"

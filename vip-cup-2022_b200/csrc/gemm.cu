@@ -1,13 +1,21 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a.  See gemm.cuh for the contract.
+// tcgen05 / TMEM / TMA GEMM + implicit-GEMM convolution for sm_100a.  See gemm.cuh for the contract.
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d (128B swizzle) of A[128 x 64] and B[BN x 64] k-blocks into a
-//               kStages-deep shared-memory ring, completion on "full" mbarriers
-//   warp 1      TMEM allocation + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//               (M=128, N=BN, K=16) x4 per k-block, tcgen05.commit releases the ring slot ("empty" mbarrier) and,
-//               after the last k-block, signals the epilogue ("tmem_full")
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias / activation / layer-scale /
-//               residual -> bf16 or fp32 global stores (each thread owns one output row)
+// Persistent kernel, one CTA per SM, static round-robin over 128 x BN output tiles.  Warp roles (320 threads):
+//   warp 0      TMA producer.  A k-blocks [128 x 64] come either from a 2-D tiled tensor map over A[M,K] or, for a
+//               convolution, from an im2col-mode tensor map over the NHWC activation (one (filter tap, 64-channel
+//               block) per k-block; padding and stride are resolved by the TMA unit, nothing is materialised).  B
+//               k-blocks [BN x 64] come from a 2-D map over the weights.  128-byte swizzle, kStages-deep smem ring,
+//               completion on "full" mbarriers.  The residual tile (if any) is also brought in by TMA, into the
+//               output staging buffers.
+//   warp 1      TMEM allocation (2 x BN fp32 columns = two accumulator stages) + MMA issuer: one lane issues
+//               tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per k-block; tcgen05.commit releases the
+//               ring slot and, after the last k-block of a tile, hands the accumulator stage to the epilogue.  The
+//               MMAs of tile i+1 run while the epilogue drains tile i.
+//   warps 2..9  epilogue (256 threads): warp w owns TMEM lanes 32*(w%4).., the two warps of a lane quarter split each
+//               64-column chunk in halves.  tcgen05.ld -> registers -> folded LayerNorm / bias / activation /
+//               layer-scale / residual -> bf16 -> swizzled smem staging -> one TMA store per 64-column chunk (rows
+//               beyond M and columns beyond N are clipped by the TMA unit).  Optional row statistics (for the
+//               LayerNorm folded into the NEXT contraction) and global-average-pool partial sums are accumulated here.
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -17,10 +25,16 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int kGemmThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kCBufBytes = BM * 128;  // 128 rows x 64 bf16
 
 struct GemmArgs {
   int M, N, K;
+  int num_kb, m_tiles, n_tiles;
+  int conv;  // 1: A operand comes from the im2col map
+  int cblocks, C, ks, stride, pad, Wo, HoWo;
   GemmEpilogue epi;
 };
 
@@ -31,6 +45,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -52,6 +69,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// im2col-mode load of [pixels x channels]: coordinates (c, w, h, n) of the first pixel's filter-window origin in the
+// input, offsets (s, r) of the filter tap
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c, int w,
+                                                   int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -92,48 +130,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below the bf16 / fp32-accumulate noise of this path): Keras'
+// 'gelu' is the exact erf form (models/gcvit/layers/feature.py:21)
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-x * x);  // erf(|v| / sqrt 2)
+  return 0.5f * v + 0.5f * fabsf(v) * e;          // 0.5 v (1 + sign(v) erf)
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // Keras 'gelu' = exact erf form
+  if (act == ACT_GELU) return gelu_erf(v);
   if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-v));
   return v;
 }
 
 template <int BN>
-struct TmemCols {
-  static constexpr int value = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+struct Cfg {
+  static constexpr int kStages = BN == 256 ? 3 : BN == 128 ? 5 : 8;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCBufs = BN / 64;
+  static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: a power of two
+  static constexpr int kSmem = kStages * kStageBytes + kCBufs * kCBufBytes + 1024 + 256;
 };
 
-template <int BN, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  constexpr int kABytes = BM * BK * 2;
-  constexpr int kBBytes = BN * BK * 2;
-  constexpr int kStageBytes = kABytes + kBBytes;
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
+  using C = Cfg<BN>;
+  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* cbuf = smem + kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cbuf + C::kCBufs * kCBufBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator stage filled by the MMAs
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator stage drained by the epilogue
+  uint64_t* rfull_bar = tempty_bar + 2;        // residual tile landed in the staging buffers
+  uint64_t* cfree_bar = rfull_bar + 1;         // staging buffers free for the next residual tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const GemmEpilogue& e = g.epi;
+  const bool has_res = e.residual != nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (e.out_bf16 != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    if (has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
+    }
+    mbar_init(rfull_bar, 1);
+    mbar_init(cfree_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(TmemCols<BN>::value)
+                 "n"(C::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -143,104 +210,230 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ================= TMA producer =================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], kStageBytes);
-        uint8_t* a_dst = smem + s * kStageBytes;
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-        tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
+        int cw = 0, ch = 0, cn = 0;
+        if (g.conv) {
+          cn = m0 / g.HoWo;
+          const int rem = m0 - cn * g.HoWo;
+          const int p0 = rem / g.Wo, q0 = rem - p0 * g.Wo;
+          cw = q0 * g.stride - g.pad;
+          ch = p0 * g.stride - g.pad;
+        }
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], C::kStageBytes);
+          uint8_t* a_dst = smem + s * C::kStageBytes;
+          if (g.conv) {
+            const int tap = kb / g.cblocks, cb = kb - tap * g.cblocks;
+            const int r = tap / g.ks, sx = tap - r * g.ks;
+            tma_load_im2col_4d(a_dst, &tmA, &full_bar[s], cb * BK, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+            tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], tap * g.C + cb * BK, n0);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+            tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0);
+          }
+        }
+        if (has_res) {
+          // after this tile's operand loads are in flight: wait until the previous tile's stores have left the
+          // staging buffers, then bring in the residual tile
+          mbar_wait(cfree_bar, (tcount & 1) ^ 1);
+          int nch = 0;
+          for (int j = 0; j < C::kCBufs; ++j) nch += (n0 + j * 64 < g.N) ? 1 : 0;
+          mbar_expect_tx(rfull_bar, nch * kCBufBytes);
+          for (int j = 0; j < nch; ++j) tma_load_2d(cbuf + j * kCBufBytes, &tmR, rfull_bar, n0 + j * 64, m0);
+        }
       }
     }
   } else if (warp == 1) {
+    // ================= MMA issuer =================
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
         tcgen05_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-        const uint64_t a_desc = make_sw128_desc(a_addr);
-        const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+          const uint64_t a_desc = make_sw128_desc(a_addr);
+          const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // implies tcgen05.fence::before_thread_sync
         }
-        umma_commit(&empty_bar[s]);  // implies tcgen05.fence::before_thread_sync
+        umma_commit(&tfull_bar[as]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
-    const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const GemmEpilogue& e = g.epi;
+    // ================= epilogue =================
+    const int te = threadIdx.x - 64;           // 0..255
+    const int quarter = warp & 3;              // TMEM lanes 32*quarter .. +31
+    const int half = (warp - 2) >> 2;          // which 32 columns of each 64-column chunk
+    const int rt = quarter * 32 + lane;        // row inside the tile
+    const uint32_t swz = (uint32_t)(rt & 7);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
+      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      const int row = m0 + rt;
+      float mean = 0.0f, rstd = 1.0f;
+      if (e.ln_stats != nullptr && row < g.M) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row);
+        const float inv = 1.0f / (float)e.ln_cols;
+        mean = st.x * inv;
+        rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.0f) + e.ln_eps);
+      }
+      mbar_wait(&tfull_bar[as], aph);
+      tcgen05_fence_after();
+      if (has_res) mbar_wait(rfull_bar, tcount & 1);
+      float rs_sum = 0.0f, rs_sq = 0.0f;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      if (row < g.M) {
-        float v[32];
+      for (int j = 0; j < C::kCBufs; ++j) {
+        if (n0 + j * 64 >= g.N) break;  // uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + j * 64 + half * 32), r);
+        uint8_t* crow = cbuf + j * kCBufBytes + rt * 128;
+        const int nb = n0 + j * 64 + half * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int n = n0 + c;
-        if (e.bias != nullptr) {
+        for (int q8 = 0; q8 < 4; ++q8) {
+          const int n = nb + q8 * 8;
+          if (n >= g.N) break;  // N % 8 == 0: a group of 8 columns is entirely inside or outside
+          float v[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
-        }
-        if (e.act != ACT_NONE) {
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q8 * 8 + i]);
+          if (e.ln_stats != nullptr) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + n));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + n) + 1);
+            const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act);
-        }
-        if (e.colscale != nullptr) {
+            for (int i = 0; i < 8; ++i) v[i] = rstd * (v[i] - mean * cs[i]);
+          }
+          if (e.bias != nullptr) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.bias + n) + 1);
+            v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
+            v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
+          }
+          if (e.act != ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= __ldg(e.colscale + n + j);
-        }
-        if (e.residual != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(e.residual + (size_t)row * e.ldr + n);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint4 u = __ldg(rp + j4);
+            for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], e.act);
+          }
+          if (e.colscale != nullptr) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.colscale + n));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.colscale + n) + 1);
+            v[0] *= c0.x; v[1] *= c0.y; v[2] *= c0.z; v[3] *= c0.w;
+            v[4] *= c1.x; v[5] *= c1.y; v[6] *= c1.z; v[7] *= c1.w;
+          }
+          uint4* cp = reinterpret_cast<uint4*>(crow + ((((uint32_t)(half * 4 + q8)) ^ swz) << 4));
+          if (has_res) {
+            const uint4 u = *cp;
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              v[j4 * 8 + 2 * t] += __uint_as_float(w[t] << 16);
-              v[j4 * 8 + 2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+              v[2 * t] += __uint_as_float(w[t] << 16);
+              v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
             }
           }
-        }
-        if (e.out_bf16 != nullptr) {
-          uint4* op = reinterpret_cast<uint4*>(e.out_bf16 + (size_t)row * e.ldc + n);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
+          if (e.out_bf16 != nullptr) {
             uint32_t w[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(v[j4 * 8 + 2 * t], v[j4 * 8 + 2 * t + 1]);
-              w[t] = *reinterpret_cast<const uint32_t*>(&h);
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+              w[t] = *reinterpret_cast<const uint32_t*>(&h2);
+              if (e.row_stats != nullptr) {
+                const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+                rs_sum += lo + hi;
+                rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
+              }
             }
-            op[j4] = make_uint4(w[0], w[1], w[2], w[3]);
+            *cp = make_uint4(w[0], w[1], w[2], w[3]);
+          } else if (row < g.M) {
+            float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
+            op[0] = make_float4(v[0], v[1], v[2], v[3]);
+            op[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
-        } else {
-          float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) op[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+        if (e.out_bf16 != nullptr) {
+          fence_async_smem();
+          epi_bar_sync();
+          if (te == 0) {
+            tma_store_2d(&tmC, cbuf + j * kCBufBytes, n0 + j * 64, m0);
+            tma_store_commit();
+          }
         }
       }
+      // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+      if (e.row_stats != nullptr && row < g.M) {
+        atomicAdd(e.row_stats + 2 * (size_t)row, rs_sum);
+        atomicAdd(e.row_stats + 2 * (size_t)row + 1, rs_sq);
+      }
+      if (e.gap != nullptr) {
+        // column sums of the staged bf16 tile, split at image boundaries: thread -> (2 columns, 16 rows)
+        const int cpair = te & 31, rq = te >> 5;
+        for (int j = 0; j < C::kCBufs; ++j) {
+          const int n = n0 + j * 64 + cpair * 2;
+          if (n0 + j * 64 >= g.N) break;
+          if (n >= g.N) continue;
+          const uint8_t* cb = cbuf + j * kCBufBytes;
+          int rr = rq * 16;
+          int img = (m0 + rr) / e.gap_rows;
+          int next = (img + 1) * e.gap_rows - m0;  // first tile row of the next image
+          float s0 = 0.0f, s1 = 0.0f;
+          for (int k = 0; k < 16; ++k, ++rr) {
+            if (m0 + rr >= g.M) break;
+            if (rr == next) {
+              atomicAdd(e.gap + (size_t)img * g.N + n, s0);
+              atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
+              s0 = s1 = 0.0f;
+              ++img;
+              next += e.gap_rows;
+            }
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(cb + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) +
+                                                                  (cpair & 3) * 4);
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xffff0000u);
+          }
+          if (m0 + rq * 16 < g.M) {
+            atomicAdd(e.gap + (size_t)img * g.N + n, s0);
+            atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
+          }
+        }
+      }
+      if (e.gap != nullptr && has_res) epi_bar_sync();  // every thread is done reading the staged tile
+      // staging buffers may be rewritten (by the next residual load or the next tile's epilogue) only after the
+      // TMA stores have finished reading them
+      if (te == 0) {
+        tma_store_wait_read();
+        if (has_res) mbar_arrive(cfree_bar);
+      }
+      epi_bar_sync();
     }
-    tcgen05_fence_before();
+    if (te == 0) tma_store_wait_all();
   }
+  tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TmemCols<BN>::value) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
   }
 }
 
@@ -248,22 +441,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
+void* driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    return p;
+  return nullptr;
 }
 
 // [rows, cols] bf16 row-major with `ld` elements between rows; box = [box_rows, 64 cols], 128B swizzle, zero OOB fill
-int make_tmap_2d(CUtensorMap* tm, const void* base, int rows, int cols, int ld, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
+int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, int ld, int box_rows) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
   VIP_REQUIRE(fn != nullptr, VIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -272,25 +465,118 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, int rows, int cols, int ld, 
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  VIP_REQUIRE(r == CUDA_SUCCESS, VIP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d)",
-              (int)r, rows, cols, ld);
+  VIP_REQUIRE(r == CUDA_SUCCESS, VIP_ERR_CUDA,
+              "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d ld=%d box_rows=%d)", (int)r, rows, cols,
+              ld, box_rows);
   return VIP_OK;
 }
 
-template <int BN, int kStages>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st) {
-  constexpr int smem = kStages * (BM * BK * 2 + BN * BK * 2) + (2 * kStages + 1) * 8 + 16 + 1024;
-  auto kern = gemm_tcgen05_kernel<BN, kStages>;
+// NHWC activation as an im2col source: box = 128 output pixels x 64 channels
+int make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& c) {
+  static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));
+  VIP_REQUIRE(fn != nullptr, VIP_ERR_CUDA, "cuTensorMapEncodeIm2col is not available from the driver");
+  const cuuint64_t gdim[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.Nimg};
+  const cuuint64_t gstride[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+  const int lower[2] = {-c.pad, -c.pad};                                        // (W, H)
+  const int upper[2] = {c.pad - (c.ksize - 1), c.pad - (c.ksize - 1)};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, lower, upper,
+                        (cuuint32_t)BK, (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VIP_REQUIRE(r == CUDA_SUCCESS, VIP_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d (N=%d H=%d W=%d C=%d k=%d s=%d p=%d)",
+              (int)r, c.Nimg, c.H, c.W, c.C, c.ksize, c.stride, c.pad);
+  return VIP_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+           const GemmArgs& g, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN>;
   static bool configured = false;  // per-process; attribute is per-function
   if (!configured) {
-    VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
     configured = true;
   }
-  dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, g);
+  const int tiles = g.m_tiles * g.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
   VIP_CUDA(cudaGetLastError());
   count_launch();
   return VIP_OK;
+}
+
+// tile width: trade column padding, wave quantisation over the SMs and per-tile efficiency
+int pick_bn(long long M, int N) {
+  const int sms = num_sms();
+  const long long mt = (M + BM - 1) / BM;
+  int best = 64;
+  double best_score = -1.0;
+  for (int bn : {256, 128, 64}) {
+    const int nt = (N + bn - 1) / bn;
+    const long long tiles = mt * nt;
+    const double col_eff = (double)N / ((double)nt * bn);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double wave_eff = (double)tiles / (waves * sms);
+    const double score = col_eff * wave_eff * (bn == 256 ? 1.0 : bn == 128 ? 0.97 : 0.88);
+    if (score > best_score) { best_score = score; best = bn; }
+  }
+  return best;
+}
+
+int check_epilogue(const GemmEpilogue& epi, int N) {
+  VIP_REQUIRE((epi.out_bf16 != nullptr) != (epi.out_f32 != nullptr), VIP_ERR_INVALID,
+              "gemm: exactly one of out_bf16 / out_f32 must be set");
+  VIP_REQUIRE(epi.ldc % 8 == 0 && epi.ldc >= N, VIP_ERR_UNSUPPORTED, "gemm: ldc must be a multiple of 8 and >= N");
+  VIP_REQUIRE(epi.residual == nullptr || (epi.ldr % 8 == 0 && ((uintptr_t)epi.residual & 15) == 0), VIP_ERR_UNSUPPORTED,
+              "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+  VIP_REQUIRE((epi.ln_stats == nullptr) == (epi.ln_colsum == nullptr), VIP_ERR_INVALID,
+              "gemm: ln_stats and ln_colsum come together");
+  VIP_REQUIRE(epi.ln_stats == nullptr || epi.ln_cols > 0, VIP_ERR_INVALID, "gemm: ln_cols must be set with ln_stats");
+  VIP_REQUIRE((epi.row_stats == nullptr && epi.gap == nullptr) || epi.out_bf16 != nullptr, VIP_ERR_UNSUPPORTED,
+              "gemm: row_stats / gap need a bf16 output");
+  VIP_REQUIRE(epi.gap == nullptr || epi.gap_rows > 0, VIP_ERR_INVALID, "gemm: gap_rows must be set with gap");
+  const void* outp = epi.out_bf16 ? (const void*)epi.out_bf16 : (const void*)epi.out_f32;
+  VIP_REQUIRE(((uintptr_t)outp & 15) == 0, VIP_ERR_INVALID, "gemm: output must be 16-byte aligned");
+  return VIP_OK;
+}
+
+int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, int N, int K, GemmArgs& g,
+        const GemmEpilogue& epi, cudaStream_t stream) {
+  const int bn = pick_bn(M, N);
+  CUtensorMap tmB, tmC, tmR;
+  int rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
+  if (rc != VIP_OK) return rc;
+  tmC = tmB;
+  tmR = tmB;
+  if (epi.out_bf16 != nullptr) {
+    rc = make_tmap_2d(&tmC, epi.out_bf16, M, N, epi.ldc, BM);
+    if (rc != VIP_OK) return rc;
+  }
+  if (epi.residual != nullptr) {
+    rc = make_tmap_2d(&tmR, epi.residual, M, N, epi.ldr, BM);
+    if (rc != VIP_OK) return rc;
+  }
+  g.M = (int)M;
+  g.N = N;
+  g.K = K;
+  g.m_tiles = (int)((M + BM - 1) / BM);
+  g.n_tiles = (N + bn - 1) / bn;
+  g.epi = epi;
+  switch (bn) {
+    case 256: return launch<256>(tmA, tmB, tmC, tmR, g, stream);
+    case 128: return launch<128>(tmA, tmB, tmC, tmR, g, stream);
+    default: return launch<64>(tmA, tmB, tmC, tmR, g, stream);
+  }
 }
 
 }  // namespace
@@ -300,48 +586,102 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, 
   VIP_REQUIRE(M > 0 && N > 0 && K > 0, VIP_ERR_INVALID, "gemm_bf16: empty problem %dx%dx%d", M, N, K);
   VIP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, VIP_ERR_UNSUPPORTED,
               "gemm_bf16: K, lda, ldb must be multiples of 8 (16-byte TMA rows): K=%d lda=%d ldb=%d", K, lda, ldb);
-  VIP_REQUIRE(N % 32 == 0, VIP_ERR_UNSUPPORTED, "gemm_bf16: N must be a multiple of 32 (N=%d)", N);
+  VIP_REQUIRE(N % 8 == 0, VIP_ERR_UNSUPPORTED, "gemm_bf16: N must be a multiple of 8 (N=%d)", N);
   VIP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, VIP_ERR_INVALID, "gemm_bf16: unaligned operand");
-  VIP_REQUIRE((epi.out_bf16 != nullptr) != (epi.out_f32 != nullptr), VIP_ERR_INVALID,
-              "gemm_bf16: exactly one of out_bf16 / out_f32 must be set");
-  VIP_REQUIRE(epi.ldc % 8 == 0 && (epi.residual == nullptr || epi.ldr % 8 == 0), VIP_ERR_UNSUPPORTED,
-              "gemm_bf16: ldc / ldr must be multiples of 8");
-  // tile width: widest of 256 / 128 / 64 / 32 that divides N and still fills the machine reasonably
-  const int mt = (M + BM - 1) / BM;
-  int bn = 32;
-  for (int cand : {256, 128, 64, 32}) {
-    if (N % cand == 0 && (cand <= 64 || (long long)mt * (N / cand) >= 120 || cand == 32)) { bn = cand; break; }
-  }
-  if (N % bn != 0) bn = 32;
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
+  int rc = check_epilogue(epi, N);
   if (rc != VIP_OK) return rc;
-  rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
+  CUtensorMap tmA;
+  rc = make_tmap_2d(&tmA, A, M, K, lda, BM);
   if (rc != VIP_OK) return rc;
-  GemmArgs g{M, N, K, epi};
-  switch (bn) {
-    case 256: return launch<256, 4>(tmA, tmB, g, stream);
-    case 128: return launch<128, 6>(tmA, tmB, g, stream);
-    case 64: return launch<64, 8>(tmA, tmB, g, stream);
-    default: return launch<32, 8>(tmA, tmB, g, stream);
-  }
+  GemmArgs g{};
+  g.num_kb = (K + BK - 1) / BK;
+  return run(tmA, B, ldb, M, N, K, g, epi, stream);
+}
+
+int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* w, int ldw, int Cout,
+                const GemmEpilogue& epi, cudaStream_t stream) {
+  VIP_REQUIRE(c.Nimg > 0 && c.H > 0 && c.W > 0 && c.C > 0 && Cout > 0, VIP_ERR_INVALID, "conv2d_bf16: empty problem");
+  VIP_REQUIRE(c.C % 8 == 0 && Cout % 8 == 0 && ldw % 8 == 0, VIP_ERR_UNSUPPORTED,
+              "conv2d_bf16: C, Cout, ldw must be multiples of 8 (C=%d Cout=%d ldw=%d)", c.C, Cout, ldw);
+  VIP_REQUIRE(c.ksize >= 1 && c.ksize <= 7 && c.stride >= 1 && c.stride <= 8 && c.pad >= 0 && c.pad < c.ksize,
+              VIP_ERR_UNSUPPORTED, "conv2d_bf16: kernel %d stride %d pad %d not supported", c.ksize, c.stride, c.pad);
+  VIP_REQUIRE(c.Ho == (c.H + 2 * c.pad - c.ksize) / c.stride + 1 && c.Wo == (c.W + 2 * c.pad - c.ksize) / c.stride + 1,
+              VIP_ERR_INVALID, "conv2d_bf16: Ho/Wo do not match the geometry");
+  VIP_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, VIP_ERR_INVALID, "conv2d_bf16: unaligned operand");
+  int rc = check_epilogue(epi, Cout);
+  if (rc != VIP_OK) return rc;
+  CUtensorMap tmA;
+  rc = make_tmap_im2col(&tmA, x, c);
+  if (rc != VIP_OK) return rc;
+  GemmArgs g{};
+  g.conv = 1;
+  g.cblocks = (c.C + BK - 1) / BK;
+  g.C = c.C;
+  g.ks = c.ksize;
+  g.stride = c.stride;
+  g.pad = c.pad;
+  g.Wo = c.Wo;
+  g.HoWo = c.Ho * c.Wo;
+  g.num_kb = c.ksize * c.ksize * g.cblocks;
+  const long long M = (long long)c.Nimg * c.Ho * c.Wo;
+  VIP_REQUIRE(M < (1LL << 31), VIP_ERR_UNSUPPORTED, "conv2d_bf16: too many output pixels");
+  return run(tmA, w, ldw, M, Cout, c.ksize * c.ksize * c.C, g, epi, stream);
 }
 
 }  // namespace vip
 
-// C-ABI test / utility entry point (also usable by a host that wants the raw contraction).
+// ---- C ABI -----------------------------------------------------------------------------------------------------
+namespace {
+vip::GemmEpilogue to_epilogue(const vip_epilogue_t* p) {
+  vip::GemmEpilogue e;
+  e.bias = p->bias;
+  e.act = p->act;
+  e.colscale = p->colscale;
+  e.residual = reinterpret_cast<const __nv_bfloat16*>(p->residual);
+  e.ldr = p->ldr;
+  e.ldc = p->ldc;
+  if (p->out_dtype == VIP_DTYPE_BF16) e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out);
+  else e.out_f32 = reinterpret_cast<float*>(p->out);
+  e.ln_stats = p->ln_stats;
+  e.ln_colsum = p->ln_colsum;
+  e.ln_cols = p->ln_cols;
+  e.ln_eps = p->ln_eps;
+  e.row_stats = p->row_stats;
+  e.gap = p->gap;
+  e.gap_rows = p->gap_rows;
+  return e;
+}
+}  // namespace
+
 extern "C" int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                              int act, const float* colscale, const void* residual, int ldr, void* out, int ldc,
                              int out_dtype, void* cuda_stream) {
-  vip::GemmEpilogue e;
-  e.bias = bias;
-  e.act = act;
-  e.colscale = colscale;
-  e.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-  e.ldr = ldr;
-  e.ldc = ldc;
-  if (out_dtype == VIP_DTYPE_BF16) e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out);
-  else e.out_f32 = reinterpret_cast<float*>(out);
+  vip_epilogue_t p{};
+  p.bias = bias;
+  p.act = act;
+  p.colscale = colscale;
+  p.residual = residual;
+  p.ldr = ldr;
+  p.out = out;
+  p.ldc = ldc;
+  p.out_dtype = out_dtype;
+  return vip_gemm_bf16_ex(A, lda, B, ldb, M, N, K, &p, cuda_stream);
+}
+
+extern "C" int vip_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                                const vip_epilogue_t* epi, void* cuda_stream) {
+  VIP_REQUIRE(A && B && epi && epi->out, VIP_ERR_INVALID, "vip_gemm_bf16_ex: null pointer");
   return vip::gemm_bf16(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb,
-                        M, N, K, e, reinterpret_cast<cudaStream_t>(cuda_stream));
+                        M, N, K, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int vip_conv2d_bf16(const void* x, int N, int H, int W, int C, const void* w, int ldw, int Cout, int ksize,
+                               int stride, int pad, const vip_epilogue_t* epi, void* cuda_stream) {
+  VIP_REQUIRE(x && w && epi && epi->out, VIP_ERR_INVALID, "vip_conv2d_bf16: null pointer");
+  vip::ConvGeom c{N, H, W, C, ksize, stride, pad, 0, 0};
+  VIP_REQUIRE(stride > 0 && ksize > 0, VIP_ERR_INVALID, "vip_conv2d_bf16: bad kernel / stride");
+  c.Ho = (H + 2 * pad - ksize) / stride + 1;
+  c.Wo = (W + 2 * pad - ksize) / stride + 1;
+  return vip::conv2d_bf16(reinterpret_cast<const __nv_bfloat16*>(x), c, reinterpret_cast<const __nv_bfloat16*>(w), ldw,
+                          Cout, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream));
 }

@@ -1,8 +1,9 @@
 // tcgen05 / TMEM / TMA GEMM core for sm_100a (hand-written PTX, no CUTLASS):
 //   D[M,N] = epilogue( A[M,K] (bf16, K-major)  x  B[N,K]^T (bf16, K-major) ),  fp32 accumulation in TMEM.
 // Used for every dense contraction of the backbones: 1x1 convolutions and Dense layers directly on NHWC
-// activations, 3x3 convolutions through an im2col view (models/resnet_rs/resnet_rs_model.py:64-84,
-// models/gcvit/layers/attention.py:25,33, models/gcvit/layers/feature.py:20-22).
+// activations, 3x3 convolutions as an implicit GEMM whose A tiles are gathered by im2col-mode TMA
+// (models/resnet_rs/resnet_rs_model.py:64-84, models/gcvit/layers/attention.py:25,33,
+// models/gcvit/layers/feature.py:20-22,98).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -13,21 +14,44 @@ namespace vip {
 enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
 
 // Epilogue, applied per output element (m, n) in this order:
-//   v = acc + bias[n];  v = act(v);  v = v * colscale[n] (layer-scale gamma);  v += residual[m, n];  store
+//   v = acc
+//   v = rstd[m] * (v - mean[m] * ln_colsum[n])      if ln_stats   (LayerNorm of the A rows folded into the contraction:
+//                                                    B must hold gamma-scaled weights, bias must hold beta @ W + b)
+//   v += bias[n];  v = act(v);  v *= colscale[n];  v += residual[m, n];  store (bf16 or f32)
+//   row_stats[m] += (sum_n out, sum_n out^2)         if row_stats  (feeds the ln_stats of the next contraction)
+//   gap[m / gap_rows, n] += out                      if gap        (GlobalAveragePooling partial sums, SE squeeze)
 struct GemmEpilogue {
-  const float* bias = nullptr;           // [N] fp32 or null
+  const float* bias = nullptr;              // [N] fp32 or null
   int act = ACT_NONE;
-  const float* colscale = nullptr;       // [N] fp32 or null
+  const float* colscale = nullptr;          // [N] fp32 or null
   const __nv_bfloat16* residual = nullptr;  // [M, ldr] bf16 or null
   int ldr = 0;
-  __nv_bfloat16* out_bf16 = nullptr;     // [M, ldc] (exactly one of out_bf16 / out_f32)
+  __nv_bfloat16* out_bf16 = nullptr;        // [M, ldc] (exactly one of out_bf16 / out_f32)
   float* out_f32 = nullptr;
   int ldc = 0;
+  const float* ln_stats = nullptr;          // [M, 2] (sum, sum of squares) of the A rows over ln_cols columns
+  const float* ln_colsum = nullptr;         // [N] column sums of the (gamma-scaled, bf16-rounded) weights
+  int ln_cols = 0;
+  float ln_eps = 1e-5f;
+  float* row_stats = nullptr;               // [M, 2] accumulated with atomics; the caller zeroes it
+  float* gap = nullptr;                     // [ceil(M / gap_rows), N] accumulated with atomics; the caller zeroes it
+  int gap_rows = 0;
 };
 
-// A: [M, K] row-major bf16 (lda elements between rows), B: [N, K] row-major bf16 (ldb).  K % 8 == 0, lda/ldb % 8 == 0,
-// 16-byte aligned bases.  N % 16 == 0.  Enqueues on `stream`; returns VIP_OK or a negative error code.
+struct ConvGeom {
+  int Nimg, H, W, C;        // input NHWC
+  int ksize, stride, pad;   // square kernel, symmetric explicit zero padding
+  int Ho, Wo;
+};
+
+// A: [M, K] row-major bf16 (lda elements between rows), B: [N, K] row-major bf16 (ldb).  K, N, lda, ldb, ldc, ldr
+// multiples of 8, 16-byte aligned bases.  Enqueues on `stream`; returns VIP_OK or a negative error code.
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
               const GemmEpilogue& epi, cudaStream_t stream);
+
+// Implicit-GEMM convolution: x bf16 NHWC, weights bf16 [Cout, ksize*ksize*C] (K order r, s, c = Keras (kh,kw,Cin,Cout)
+// flattened over its first three axes, ldw elements between rows), output rows = N*Ho*Wo pixels.  C % 8 == 0.
+int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& geom, const __nv_bfloat16* w, int ldw, int Cout,
+                const GemmEpilogue& epi, cudaStream_t stream);
 
 }  // namespace vip

@@ -176,7 +176,7 @@ __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __
 // ---- LayerNormalization(axis=-1, eps) over [M, C] (block.py:28,39; feature.py:100-101; gcvit.py:79): warp per token
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        long long M, int C, float eps) {
+                                                        float* __restrict__ row_stats, long long M, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const float rstd = rsqrtf(v / (float)C + eps);
+    float os = 0.0f, oq = 0.0f;  // statistics of the rounded output row (for a LayerNorm folded into the next GEMM)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c8 = lane + 32 * j;
@@ -220,8 +221,26 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           o8[k] = (f[j][k] - mean) * rstd * __ldg(gamma + c8 * 8 + k) + __ldg(beta + c8 * 8 + k);
-        *reinterpret_cast<bf16x8*>(out + m * C + c8 * 8) = pack8(o8);
+        const bf16x8 pk = pack8(o8);
+        *reinterpret_cast<bf16x8*>(out + m * C + c8 * 8) = pk;
+        if (row_stats != nullptr) {
+          float r8[8];
+          unpack8(pk, r8);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            os += r8[k];
+            oq = fmaf(r8[k], r8[k], oq);
+          }
+        }
       }
+    }
+    if (row_stats != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        os += __shfl_xor_sync(0xffffffffu, os, o);
+        oq += __shfl_xor_sync(0xffffffffu, oq, o);
+      }
+      if (lane == 0) *reinterpret_cast<float2*>(row_stats + 2 * m) = make_float2(os, oq);
     }
   }
 }
@@ -341,6 +360,12 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
     out[i] = __float2bfloat16_rn(x[i]);
 }
 
+// ---- out = bf16(x * scale): pooled sums -> means as a GEMM operand (SE squeeze, resnet_rs_model.py:149)
+__global__ void scale_cast_f32_bf16_kernel(const float* __restrict__ x, float scale, bf16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(x[i] * scale);
+}
+
 }  // namespace
 }  // namespace vip
 
@@ -395,11 +420,11 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, long long M, int C,
-                                  float eps, void* stream) {
+extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats,
+                                  long long M, int C, float eps, void* stream) {
   VIP_REQUIRE(x && out && gamma && beta && C % 8 == 0 && C <= 1024, VIP_ERR_INVALID,
               "vip_layernorm_bf16: bad argument (C %% 8 == 0, C <= 1024)");
-  layernorm_kernel<<<grid_for(M * 32, 256), 256, 0, ST(stream)>>>((const bf16*)x, gamma, beta, (bf16*)out, M, C, eps);
+  layernorm_kernel<<<grid_for(M * 32, 256), 256, 0, ST(stream)>>>((const bf16*)x, gamma, beta, (bf16*)out, row_stats, M, C, eps);
   LAUNCH_CHECK();
 }
 
@@ -423,6 +448,12 @@ extern "C" int vip_head_f32(const float* feat, const float* w, const float* b, f
                             double acc_weight, int N, int C, int k, int sigmoid_head, void* stream) {
   VIP_REQUIRE(feat && w && b && probs && k >= 1 && k <= 8, VIP_ERR_INVALID, "vip_head_f32: bad argument (1 <= k <= 8)");
   head_kernel<<<(N * 32 + 127) / 128, 128, 0, ST(stream)>>>(feat, w, b, probs, acc, acc_weight, N, C, k, sigmoid_head);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* stream) {
+  VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_f32_bf16: null pointer");
+  scale_cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, scale, (bf16*)out, n);
   LAUNCH_CHECK();
 }
 

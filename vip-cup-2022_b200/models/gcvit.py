@@ -73,6 +73,18 @@ class GCViT:
         k = k.reshape(-1, k.shape[-1])
         return self._bf(k.T), (self._f32(W[name + "/bias"]) if bias else None)
 
+    def _dense_ln(self, W, name, norm):
+        """Dense preceded by LayerNormalization ``norm``, packed for the folded-LN contraction (vip_epilogue_t.ln_stats):
+        LN(x) W + b = rstd (x (gamma W) - mean colsum(gamma W)) + (beta W + b).  Returns (weights bf16 [out,in], bias',
+        colsum of the bf16-rounded scaled weights)."""
+        k = np.asarray(W[name + "/kernel"], np.float32)
+        k = k.reshape(-1, k.shape[-1])                                   # (in, out)
+        gamma, beta = np.asarray(W[norm + "/gamma"], np.float32), np.asarray(W[norm + "/beta"], np.float32)
+        wg = torch.from_numpy(np.ascontiguousarray((k * gamma[:, None]).T)).to(torch.bfloat16)   # [out, in], host
+        colsum = wg.float().sum(1).contiguous().to(self.device)          # of the ROUNDED weights: the algebra stays exact
+        bias = self._f32(beta @ k + np.asarray(W[name + "/bias"], np.float32))
+        return wg.to(self.device).contiguous(), bias, colsum
+
     def _conv3(self, W, name, bias=False):
         k = np.asarray(W[name + "/kernel"], np.float32)  # (3,3,Cin,Cout)
         w2 = _pad_cols(k.reshape(-1, k.shape[3]).T, 8)
@@ -172,8 +184,8 @@ class GCViT:
                 p[f"b{i}_{j}"] = dict(
                     n1=(self._f32(W[n + "/norm1/gamma"]), self._f32(W[n + "/norm1/beta"])),
                     n2=(self._f32(W[n + "/norm2/gamma"]), self._f32(W[n + "/norm2/beta"])),
-                    qkv=self._dense(W, n + "/attn/qkv"), proj=self._dense(W, n + "/attn/proj"),
-                    fc1=self._dense(W, n + "/mlp/fc1"), fc2=self._dense(W, n + "/mlp/fc2"),
+                    qkv=self._dense_ln(W, n + "/attn/qkv", n + "/norm1"), proj=self._dense(W, n + "/attn/proj"),
+                    fc1=self._dense_ln(W, n + "/mlp/fc1", n + "/norm2"), fc2=self._dense(W, n + "/mlp/fc2"),
                     rel=self._f32(table),
                     g1=self._f32(W[n + "/gamma1"]) if n + "/gamma1" in W else None,
                     g2=self._f32(W[n + "/gamma2"]) if n + "/gamma2" in W else None)
@@ -195,22 +207,24 @@ class GCViT:
         y = nn.scale_add_act(y, gate, None, out=y)
         return nn.gemm(y.view(-1, c), d["pw"], residual=x.view(-1, c)).view(b, h, w, c)
 
-    def _reduce_apply(self, x, d, stride):
+    def _reduce_apply(self, x, d, stride, out_stats=None):
         x = nn.layernorm(x, *d["n1"], eps=LN_EPS)
         x = self._mb_apply(x, d)
         x = nn.conv2d(x, d["red"], None, ksize=3, stride=stride, pad=1)
-        return nn.layernorm(x, *d["n2"], eps=LN_EPS)
+        return nn.layernorm(x, *d["n2"], eps=LN_EPS, row_stats=out_stats)
 
-    def _block(self, x, d, heads, ws, q_global):
+    def _block(self, x, stats, d, heads, ws, q_global, st_mid, st_out):
+        """GCViTBlock (block.py:60-81).  Both LayerNorms are folded into the contraction that consumes them: ``stats`` holds
+        (sum, sum^2) of the rows of x, the proj / fc2 epilogues emit the statistics of their outputs."""
         b, h, w, c = x.shape
         x2 = x.view(-1, c)
-        t = nn.layernorm(x2, *d["n1"], eps=LN_EPS)
-        qkv = nn.gemm(t, *d["qkv"])
+        wq, bq, cq = d["qkv"]
+        qkv = nn.gemm(x2, wq, bias=bq, ln_stats=stats, ln_colsum=cq, ln_cols=c, ln_eps=LN_EPS)
         a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
-        x2 = nn.gemm(a, *d["proj"], colscale=d["g1"], residual=x2)
-        t = nn.layernorm(x2, *d["n2"], eps=LN_EPS)
-        hdn = nn.gemm(t, *d["fc1"], act="gelu")
-        x2 = nn.gemm(hdn, *d["fc2"], colscale=d["g2"], residual=x2)
+        x2 = nn.gemm(a, *d["proj"], colscale=d["g1"], residual=x2, row_stats=st_mid)
+        w1, b1, c1 = d["fc1"]
+        hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
+        x2 = nn.gemm(hdn, *d["fc2"], colscale=d["g2"], residual=x2, row_stats=st_out)
         return x2.view(b, h, w, c)
 
     def features(self, x, taps=None):
@@ -218,7 +232,14 @@ class GCViT:
         if p is None:
             raise RuntimeError("load_weights() first")
         x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
-        x = self._reduce_apply(x, p["conv_down"], self.first_strides)
+        nimg = x.shape[0]
+
+        def level_stats(i, tokens):  # one zeroed arena per level: [1 + 2*depth, tokens, 2]
+            return nn.zero_(torch.empty((1 + 2 * cfg["depths"][i], tokens, 2), dtype=torch.float32, device=x.device))
+
+        h0 = (x.shape[1] + 2 - 3) // self.first_strides + 1
+        st = level_stats(0, nimg * h0 * h0)
+        x = self._reduce_apply(x, p["conv_down"], self.first_strides, out_stats=st[0])
         if taps is not None:
             taps["stem"] = x
         for i, depth in enumerate(cfg["depths"]):
@@ -234,9 +255,11 @@ class GCViT:
                     q = nn.maxpool3s2(q)
             q = q.view(b, ws * ws, c)
             for j in range(depth):
-                x = self._block(x, p[f"b{i}_{j}"], heads, ws, q if j % 2 else None)
+                x = self._block(x, st[2 * j], p[f"b{i}_{j}"], heads, ws, q if j % 2 else None, st[2 * j + 1], st[2 * j + 2])
             if i < 3:
-                x = self._reduce_apply(x, p[f"down{i}"], 2)
+                ho = (h + 2 - 3) // 2 + 1
+                st = level_stats(i + 1, b * ho * ho)
+                x = self._reduce_apply(x, p[f"down{i}"], 2, out_stats=st[0])
             if taps is not None:
                 taps[f"level{i}"] = x
         return x

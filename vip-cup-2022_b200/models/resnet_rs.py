@@ -122,7 +122,7 @@ class ResNetRS:
         self.p = p
         return self
 
-    def _bottleneck(self, x, n, strides, use_projection):
+    def _bottleneck(self, x, n, strides, use_projection, gap):
         p = self.p
         shortcut = x
         if use_projection:
@@ -130,8 +130,11 @@ class ResNetRS:
             shortcut = nn.conv2d(s_in, *p[n + "proj"])
         y = nn.conv2d(x, *p[n + "conv1"], act="relu")
         y = nn.conv2d(y, *p[n + "conv2"], ksize=3, stride=strides, pad=1, act="relu")
-        y = nn.conv2d(y, *p[n + "conv3"])
-        pooled, _ = nn.global_avgpool(y)
+        # conv3 + folded BN; the SE squeeze (GlobalAveragePooling2D, resnet_rs_model.py:149) is accumulated by the
+        # GEMM epilogue, so the 4f-channel map is not read again before the excite pass
+        b, h, w, _ = y.shape
+        y = nn.conv2d(y, *p[n + "conv3"], gap=gap, gap_rows=h * w)
+        pooled = nn.scale_cast_bf16(gap, 1.0 / (h * w))
         hid = nn.gemm(pooled, *p[n + "se1"], act="relu")
         gate = nn.gemm(hid, *p[n + "se2"], act="sigmoid", out_dtype=torch.float32)
         return nn.scale_add_act(y, gate, shortcut, act="relu", out=y)
@@ -145,9 +148,15 @@ class ResNetRS:
             x = nn.conv2d(x, *p[f"stem{i}"], ksize=3, stride=s, pad=1, act="relu")
         if taps is not None:
             taps["stem"] = x
+        nimg = x.shape[0]
+        nblocks = sum(r for _, r in BLOCK_ARGS[self.depth])
+        gaps = nn.zero_(torch.empty((nblocks, nimg, 2048), dtype=torch.float32, device=x.device))  # one memset
+        k = 0
         for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
             for bi in range(reps):
-                x = self._bottleneck(x, f"c{gi + 2}_block_{bi}_", (1 if gi == 0 else 2) if bi == 0 else 1, bi == 0)
+                gap = gaps[k].view(-1)[: nimg * 4 * f].view(nimg, 4 * f)
+                k += 1
+                x = self._bottleneck(x, f"c{gi + 2}_block_{bi}_", (1 if gi == 0 else 2) if bi == 0 else 1, bi == 0, gap)
             if taps is not None:
                 taps[f"c{gi + 2}"] = x
         return x

@@ -26,39 +26,69 @@ def _chk(t, name, dtype=BF16):
         raise VipError(f"{name} must be a contiguous CUDA {dtype} tensor")
 
 
-def gemm(a, w, bias=None, act=None, colscale=None, residual=None, out=None, out_dtype=BF16):
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) * colscale + residual  (tcgen05 kernel, fp32 accumulation)."""
-    _chk(a, "a"), _chk(w, "w"), _chk(residual, "residual")
-    _chk(bias, "bias", torch.float32), _chk(colscale, "colscale", torch.float32)
+def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=None, ln_colsum=None, ln_cols=0,
+              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0):
+    _chk(residual, "residual")
+    for name, t in (("bias", bias), ("colscale", colscale), ("ln_stats", ln_stats), ("ln_colsum", ln_colsum),
+                    ("row_stats", row_stats), ("gap", gap)):
+        _chk(t, name, torch.float32)
+    e = _lib.Epilogue()
+    e.bias, e.act, e.colscale = _p(bias), ACT[act], _p(colscale)
+    e.residual, e.ldr = _p(residual), (0 if residual is None else residual.stride(0))
+    e.out, e.ldc = _p(out), out.stride(0)
+    e.out_dtype = _lib.VIP_DTYPE_BF16 if out.dtype == BF16 else _lib.VIP_DTYPE_F32
+    e.ln_stats, e.ln_colsum, e.ln_cols, e.ln_eps = _p(ln_stats), _p(ln_colsum), int(ln_cols), float(ln_eps)
+    e.row_stats, e.gap, e.gap_rows = _p(row_stats), _p(gap), int(gap_rows)
+    return e
+
+
+def gemm(a, w, bias=None, act=None, colscale=None, residual=None, out=None, out_dtype=BF16, **fused):
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T)  (persistent tcgen05 kernel, fp32 accumulation).  ``fused`` takes the
+    vip_epilogue_t extras: ln_stats / ln_colsum / ln_cols / ln_eps (LayerNorm folded into this contraction), row_stats
+    (statistics of the output rows for the next folded LayerNorm), gap / gap_rows (global-average-pool partial sums)."""
+    _chk(a, "a"), _chk(w, "w")
     m, k = a.shape
     n = w.shape[0]
     if w.shape[1] != k:
         raise VipError(f"gemm: K mismatch {a.shape} x {w.shape}")
     if out is None:
         out = torch.empty((m, n), dtype=out_dtype, device=a.device)
-    rc = _lib.lib().vip_gemm_bf16(_p(a), a.stride(0), _p(w), w.stride(0), m, n, k, _p(bias), ACT[act], _p(colscale),
-                                  _p(residual), 0 if residual is None else residual.stride(0), _p(out), out.stride(0),
-                                  _lib.VIP_DTYPE_BF16 if out.dtype == BF16 else _lib.VIP_DTYPE_F32, _st())
-    _lib.check(rc, "vip_gemm_bf16")
+    e = _epilogue(out, bias, act, colscale, residual, **fused)
+    rc = _lib.lib().vip_gemm_bf16_ex(_p(a), a.stride(0), _p(w), w.stride(0), m, n, k, e, _st())
+    _lib.check(rc, "vip_gemm_bf16_ex")
     return out
 
 
-def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None):
-    """x bf16 [N,H,W,C]; w bf16 [Cout, Kp] with K order (r,s,c). Returns bf16 [N,Ho,Wo,Cout]."""
-    _chk(x, "x")
+def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, **fused):
+    """x bf16 [N,H,W,C]; w bf16 [Cout, Kp] with K order (r,s,c). Returns bf16 [N,Ho,Wo,Cout].
+    1x1 stride 1: plain GEMM on the NHWC activation; C % 8 == 0: implicit GEMM (im2col-mode TMA, nothing materialised);
+    otherwise (the 3-channel network input): explicit im2col matrix + GEMM."""
+    _chk(x, "x"), _chk(w, "w")
     n, h, wd, c = x.shape
     ho = (h + 2 * pad - ksize) // stride + 1
     wo = (wd + 2 * pad - ksize) // stride + 1
+    cout = w.shape[0]
+    res2 = None if residual is None else residual.view(n * ho * wo, -1)
     if ksize == 1 and stride == 1 and pad == 0 and w.shape[1] == c:
-        a = x.view(n * h * wd, c)
+        y = gemm(x.view(n * h * wd, c), w, bias=bias, act=act, residual=res2, **fused)
+    elif c % 8 == 0 and w.shape[1] == ksize * ksize * c:
+        y = torch.empty((n * ho * wo, cout), dtype=BF16, device=x.device)
+        e = _epilogue(y, bias, act, None, res2, **fused)
+        rc = _lib.lib().vip_conv2d_bf16(_p(x), n, h, wd, c, _p(w), w.stride(0), cout, ksize, stride, pad, e, _st())
+        _lib.check(rc, "vip_conv2d_bf16")
     else:
         kp = w.shape[1]
         a = torch.empty((n * ho * wo, kp), dtype=BF16, device=x.device)
         rc = _lib.lib().vip_im2col_bf16(_p(x), n, h, wd, c, ksize, stride, pad, ho, wo, _p(a), kp, _st())
         _lib.check(rc, "vip_im2col_bf16")
-    res2 = None if residual is None else residual.view(n * ho * wo, -1)
-    y = gemm(a, w, bias=bias, act=act, residual=res2)
-    return y.view(n, ho, wo, w.shape[0])
+        y = gemm(a, w, bias=bias, act=act, residual=res2, **fused)
+    return y.view(n, ho, wo, cout)
+
+
+def zero_(t):
+    """cudaMemsetAsync(0) on the current stream (accumulators of the fused row-statistics / pooling epilogues)."""
+    _lib.check(_lib.lib().vip_memset_async(_p(t), 0, t.numel() * t.element_size(), _st()), "vip_memset_async")
+    return t
 
 
 def avgpool2_same(x):
@@ -91,12 +121,13 @@ def scale_add_act(y, gate=None, shortcut=None, act=None, out=None):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5):
+def layernorm(x, gamma, beta, eps=1e-5, row_stats=None):
     _chk(x, "x"), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32)
+    _chk(row_stats, "row_stats", torch.float32)
     c = x.shape[-1]
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // c, c, eps, _st()),
-               "vip_layernorm_bf16")
+    _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), _p(row_stats), x.numel() // c, c, eps,
+                                             _st()), "vip_layernorm_bf16")
     return out
 
 
@@ -140,4 +171,12 @@ def cast_bf16(x_f32):
     _chk(x_f32, "x", torch.float32)
     out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
     _lib.check(_lib.lib().vip_cast_f32_bf16(_p(x_f32), _p(out), x_f32.numel(), _st()), "vip_cast_f32_bf16")
+    return out
+
+
+def scale_cast_bf16(x_f32, scale):
+    _chk(x_f32, "x", torch.float32)
+    out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
+    _lib.check(_lib.lib().vip_scale_cast_f32_bf16(_p(x_f32), float(scale), _p(out), x_f32.numel(), _st()),
+               "vip_scale_cast_f32_bf16")
     return out
