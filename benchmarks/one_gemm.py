@@ -1,0 +1,27 @@
+#!/usr/bin/env python
+"""One contraction launch for ncu: python benchmarks/one_gemm.py M N K [extras: ln gelu res gap<HW>] | conv H C Cout stride"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vipcup_b200 import nn
+dev = torch.device("cuda:0")
+rnd = lambda *s: (torch.randn(*s, device=dev) * 0.1).to(torch.bfloat16)
+a = sys.argv[1:]
+if a[0] == "conv":
+    h, c, co, s = map(int, a[1:5]); B = 256
+    x, w, bias = rnd(B, h, h, c), rnd(co, 9 * c), torch.randn(co, device=dev)
+    fn = lambda: nn.conv2d(x, w, bias, ksize=3, stride=s, pad=1, act="relu")
+else:
+    m, n, k = map(int, a[:3]); ex = a[3:]
+    A, w, bias = rnd(m, k), rnd(n, k), torch.randn(n, device=dev)
+    kw = {}
+    if "ln" in ex: kw.update(ln_stats=torch.rand(m, 2, device=dev) + torch.tensor([0.0, 70.0], device=dev), ln_colsum=torch.randn(n, device=dev), ln_cols=k)
+    if "gelu" in ex: kw.update(act="gelu")
+    if "res" in ex: kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 2, device=dev))
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=dev)
+    fn = lambda: nn.gemm(A, w, bias=bias, out=out, **kw)
+for _ in range(3): fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+print("us", e0.elapsed_time(e1) * 1e3)

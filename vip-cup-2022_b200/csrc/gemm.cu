@@ -26,15 +26,27 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
 constexpr int kThreads = 320;
-constexpr int kEpiThreads = 256;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kCBufBytes = BM * 128;  // 128 rows x 64 bf16
+constexpr int kMaxCols = 8192;        // widest N the neutral-parameter vectors cover
+
+// Neutral per-column parameter vectors: an absent bias / ln_colsum points at zeros, an absent colscale at ones, so the
+// epilogue inner loop carries no per-feature branches.
+__device__ float g_zeros[kMaxCols];
+__device__ float g_ones[kMaxCols];
+__global__ void init_neutral_kernel() {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaxCols; i += gridDim.x * blockDim.x) {
+    g_zeros[i] = 0.0f;
+    g_ones[i] = 1.0f;
+  }
+}
 
 struct GemmArgs {
   int M, N, K;
   int num_kb, m_tiles, n_tiles;
   int conv;  // 1: A operand comes from the im2col map
   int cblocks, C, ks, stride, pad, Wo, HoWo;
+  int mode;  // EpiMode
   GemmEpilogue epi;
 };
 
@@ -85,7 +97,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -130,51 +141,132 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below the bf16 / fp32-accumulate noise of this path): Keras'
-// 'gelu' is the exact erf form (models/gcvit/layers/feature.py:21)
-__device__ __forceinline__ float gelu_erf(float v) {
-  const float x = fabsf(v) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-x * x);  // erf(|v| / sqrt 2)
-  return 0.5f * v + 0.5f * fabsf(v) * e;          // 0.5 v (1 + sign(v) erf)
-}
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_GELU) return gelu_erf(v);
-  if (act == ACT_SIGMOID) return 1.0f / (1.0f + __expf(-v));
-  return v;
+// GELU.  Keras' 'gelu' is the exact erf form (models/gcvit/layers/feature.py:21).  Evaluated as
+//   x * Phi(x),  Phi(x) = 0.5 (1 + tanh(x (a0 + a1 x^2 + a2 x^4)))
+// with (a0, a1, a2) fitted to atanh(erf(x / sqrt 2)) (max |formula error| 2.6e-5 over all x; the textbook two-term tanh
+// form is 20x worse) and the hardware tanh.approx.f32 (relative error 2^-11): |error| <= 3e-4 |x|, 0.07 ulp of the bf16
+// value the result is stored as.  One MUFU + 7 FMA-pipe instructions: the erf / exp forms need two MUFU per element,
+// which makes the fc1 epilogues MUFU-bound (16 results / clock / SM).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 64.0f);  // the fitted polynomial is monotone up to |x| = 8, where tanh has saturated
+  float p = fmaf(-0.00035307545f, x2, 0.037015257f);
+  p = fmaf(p, x2, 0.79749725f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
-template <int BN>
+// kDeep: one CTA per SM with a deep operand ring (long K loops).  !kDeep: two CTAs per SM with a short ring, for the
+// output-heavy contractions (K <= 256) whose time goes into the epilogue; BN <= 128 so that both CTAs get TMEM.
+template <int BN, bool kDeep>
 struct Cfg {
-  static constexpr int kStages = BN == 256 ? 3 : BN == 128 ? 5 : 8;
+  static constexpr int kStages = kDeep ? (BN == 256 ? 3 : BN == 128 ? 5 : 6) : (BN == 128 ? 2 : 3);
+  static constexpr int kCBufs = kDeep ? 4 : 2;   // ring of output staging buffers (one 64-column chunk each)
+  static constexpr int kMinBlocks = kDeep ? 1 : 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kCBufs = BN / 64;
+  static constexpr int kChunks = BN / 64;   // 64-column chunks per tile
   static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: a power of two
   static constexpr int kSmem = kStages * kStageBytes + kCBufs * kCBufBytes + 1024 + 256;
+  static_assert(kDeep || BN <= 128, "two CTAs per SM need at most 256 TMEM columns each");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+// One group of 8 output columns of one row: folded LayerNorm + bias (2 FMAs), activation, column scale.
+template <int ACT>
+__device__ __forceinline__ void epi_group(float (&v)[8], float rstd, float nmr, const float* __restrict__ colsum,
+                                          const float* __restrict__ bias, const float* __restrict__ colscale, int n) {
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(colsum + n)), s1 = __ldg(reinterpret_cast<const float4*>(colsum + n) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n) + 1);
+  const float4 c0 = __ldg(reinterpret_cast<const float4*>(colscale + n)), c1 = __ldg(reinterpret_cast<const float4*>(colscale + n) + 1);
+  const float cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float sc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = fmaf(v[i], rstd, fmaf(nmr, cs[i], bs[i]));  // rstd * (acc - mean * colsum) + bias
+    if (ACT == ACT_RELU) t = fmaxf(t, 0.0f);
+    if (ACT == ACT_GELU) t = gelu_fast(t);
+    if (ACT == ACT_SIGMOID) t = 1.0f / (1.0f + __expf(-t));
+    v[i] = t * sc[i];
+  }
+}
+
+// Specialised epilogues (compile-time feature sets) for the combinations the backbones use; everything else takes the
+// generic path with neutral parameter vectors.
+enum EpiMode : int { EPI_GENERIC = 0, EPI_NONE, EPI_RELU, EPI_GELU, EPI_LN, EPI_LN_GELU, EPI_RES };
+
+// 32 columns of one output row: TMEM registers -> (folded LN) + bias -> activation -> (+ residual, row statistics) ->
+// bf16 -> swizzled staging row.  `nb` = first column, `cbase16` = 16-byte chunk index of that column inside the row.
+template <int MODE>
+__device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
+                                          int N, float rstd, float nmr, const float* __restrict__ colsum,
+                                          const float* __restrict__ bias, float& rs_sum, float& rs_sq) {
+  constexpr bool kLN = MODE == EPI_LN || MODE == EPI_LN_GELU;
+  constexpr bool kGelu = MODE == EPI_GELU || MODE == EPI_LN_GELU;
+#pragma unroll
+  for (int q8 = 0; q8 < 4; ++q8) {
+    const int n = nb + q8 * 8;
+    if (n >= N) break;  // N % 8 == 0: a group of 8 columns is entirely inside or outside
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(bias + n) + 1);
+    float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    if (kLN) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(colsum + n)), s1 = __ldg(reinterpret_cast<const float4*>(colsum + n) + 1);
+      const float cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh[i] = fmaf(nmr, cs[i], sh[i]);
+    }
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = __uint_as_float(r[q8 * 8 + i]);
+      float t = kLN ? fmaf(a, rstd, sh[i]) : a + sh[i];
+      if (MODE == EPI_RELU) t = fmaxf(t, 0.0f);
+      if (kGelu) t = gelu_fast(t);
+      v[i] = t;
+    }
+    uint4* cp = reinterpret_cast<uint4*>(crow + ((cbase16 + q8) ^ swz) * 16);
+    if (MODE == EPI_RES) {
+      const uint4 u = *cp;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        v[2 * t] += __uint_as_float(w[t] << 16);
+        v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rs_sum += v[i];
+        rs_sq = fmaf(v[i], v[i], rs_sq);
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+      w[t] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *cp = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int BN, bool kDeep>
+__global__ void __launch_bounds__(kThreads, Cfg<BN, kDeep>::kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kDeep>;
   constexpr int kStages = C::kStages;
+  constexpr int kCBufs = C::kCBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* cbuf = smem + kStages * C::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cbuf + C::kCBufs * kCBufBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cbuf + kCBufs * kCBufBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator stage filled by the MMAs
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator stage drained by the epilogue
-  uint64_t* rfull_bar = tempty_bar + 2;        // residual tile landed in the staging buffers
-  uint64_t* cfree_bar = rfull_bar + 1;         // staging buffers free for the next residual tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree_bar + 1);
+  uint64_t* rfull_bar = tempty_bar + 2;        // [kCBufs] residual chunk landed in a staging buffer
+  uint64_t* cfree_bar = rfull_bar + kCBufs;    // [kCBufs] staging buffer free for the next residual chunk
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree_bar + kCBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.m_tiles * g.n_tiles;
@@ -194,8 +286,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
     }
-    mbar_init(rfull_bar, 1);
-    mbar_init(cfree_bar, 1);
+    for (int b = 0; b < kCBufs; ++b) {
+      mbar_init(&rfull_bar[b], 1);
+      mbar_init(&cfree_bar[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -212,8 +306,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      uint32_t it = 0, cc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
         int cw = 0, ch = 0, cn = 0;
         if (g.conv) {
@@ -240,13 +334,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (has_res) {
-          // after this tile's operand loads are in flight: wait until the previous tile's stores have left the
-          // staging buffers, then bring in the residual tile
-          mbar_wait(cfree_bar, (tcount & 1) ^ 1);
-          int nch = 0;
-          for (int j = 0; j < C::kCBufs; ++j) nch += (n0 + j * 64 < g.N) ? 1 : 0;
-          mbar_expect_tx(rfull_bar, nch * kCBufBytes);
-          for (int j = 0; j < nch; ++j) tma_load_2d(cbuf + j * kCBufBytes, &tmR, rfull_bar, n0 + j * 64, m0);
+          // after this tile's operand loads are in flight: bring the residual chunks into the staging ring, each as
+          // soon as the store that last used its buffer has finished reading it
+          for (int j = 0; j < C::kChunks && n0 + j * 64 < g.N; ++j, ++cc) {
+            const uint32_t b = cc % kCBufs, u = cc / kCBufs;
+            mbar_wait(&cfree_bar[b], (u & 1) ^ 1);
+            mbar_expect_tx(&rfull_bar[b], kCBufBytes);
+            tma_load_2d(cbuf + b * kCBufBytes, &tmR, &rfull_bar[b], n0 + j * 64, m0);
+          }
         }
       }
     }
@@ -286,29 +381,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 2) >> 2;          // which 32 columns of each 64-column chunk
     const int rt = quarter * 32 + lane;        // row inside the tile
     const uint32_t swz = (uint32_t)(rt & 7);
-    uint32_t tcount = 0;
+    const float* p_colsum = e.ln_colsum != nullptr ? e.ln_colsum : g_zeros;
+    const float* p_bias = e.bias != nullptr ? e.bias : g_zeros;
+    const float* p_colscale = e.colscale != nullptr ? e.colscale : g_ones;
+    uint32_t tcount = 0, cc = 0;  // tiles and 64-column chunks processed by this CTA
+    // row statistics of the folded LayerNorm: fetched one tile ahead so that the load never sits on the critical path
+    auto load_stats = [&](int tile_) -> float2 {
+      const long long row_ = (long long)(tile_ / g.n_tiles) * BM + rt;
+      if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return make_float2(0.0f, 0.0f);
+      return __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row_);
+    };
+    float2 st_next = load_stats(blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       const int row = m0 + rt;
-      float mean = 0.0f, rstd = 1.0f;
-      if (e.ln_stats != nullptr && row < g.M) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row);
+      float rstd = 1.0f, nmr = 0.0f;  // 1/sigma and -mean/sigma of this row (identity without a folded LayerNorm)
+      if (e.ln_stats != nullptr) {
+        const float2 st = st_next;
+        st_next = load_stats(tile + gridDim.x);
         const float inv = 1.0f / (float)e.ln_cols;
-        mean = st.x * inv;
+        const float mean = st.x * inv;
         rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.0f) + e.ln_eps);
+        nmr = -mean * rstd;
       }
       mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
-      if (has_res) mbar_wait(rfull_bar, tcount & 1);
       float rs_sum = 0.0f, rs_sq = 0.0f;
 #pragma unroll 1
-      for (int j = 0; j < C::kCBufs; ++j) {
+      for (int j = 0; j < C::kChunks; ++j, ++cc) {
         if (n0 + j * 64 >= g.N) break;  // uniform
+        const uint32_t b = cc % kCBufs;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + j * 64 + half * 32), r);
-        uint8_t* crow = cbuf + j * kCBufBytes + rt * 128;
+        if (j == C::kChunks - 1 || n0 + (j + 1) * 64 >= g.N) {
+          // last TMEM read of this accumulator stage: hand it back to the MMA warp before the math
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (has_res) mbar_wait(&rfull_bar[b], (cc / kCBufs) & 1);
+        uint8_t* cbase = cbuf + b * kCBufBytes;
+        uint8_t* crow = cbase + rt * 128;
         const int nb = n0 + j * 64 + half * 32;
+        if (g.mode != EPI_GENERIC) {
+          const uint32_t c16 = (uint32_t)(half * 4);
+          switch (g.mode) {
+            case EPI_NONE: epi_row32<EPI_NONE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_RELU: epi_row32<EPI_RELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_GELU: epi_row32<EPI_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            default: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+          }
+        } else
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
           const int n = nb + q8 * 8;
@@ -316,28 +442,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q8 * 8 + i]);
-          if (e.ln_stats != nullptr) {
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + n));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.ln_colsum + n) + 1);
-            const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = rstd * (v[i] - mean * cs[i]);
-          }
-          if (e.bias != nullptr) {
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.bias + n) + 1);
-            v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
-            v[4] += c1.x; v[5] += c1.y; v[6] += c1.z; v[7] += c1.w;
-          }
-          if (e.act != ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], e.act);
-          }
-          if (e.colscale != nullptr) {
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(e.colscale + n));
-            const float4 c1 = __ldg(reinterpret_cast<const float4*>(e.colscale + n) + 1);
-            v[0] *= c0.x; v[1] *= c0.y; v[2] *= c0.z; v[3] *= c0.w;
-            v[4] *= c1.x; v[5] *= c1.y; v[6] *= c1.z; v[7] *= c1.w;
+          switch (e.act) {
+            case ACT_RELU: epi_group<ACT_RELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+            case ACT_GELU: epi_group<ACT_GELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+            case ACT_SIGMOID: epi_group<ACT_SIGMOID>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+            default: epi_group<ACT_NONE>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
           }
           uint4* cp = reinterpret_cast<uint4*>(crow + ((((uint32_t)(half * 4 + q8)) ^ swz) << 4));
           if (has_res) {
@@ -355,11 +464,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int t = 0; t < 4; ++t) {
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
               w[t] = *reinterpret_cast<const uint32_t*>(&h2);
-              if (e.row_stats != nullptr) {
-                const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
-                rs_sum += lo + hi;
-                rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
-              }
+              const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+              rs_sum += lo + hi;
+              rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
             }
             *cp = make_uint4(w[0], w[1], w[2], w[3]);
           } else if (row < g.M) {
@@ -368,64 +475,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             op[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
-        if (e.out_bf16 != nullptr) {
-          fence_async_smem();
-          epi_bar_sync();
-          if (te == 0) {
-            tma_store_2d(&tmC, cbuf + j * kCBufBytes, n0 + j * 64, m0);
-            tma_store_commit();
-          }
+        // The chunk is staged.  Before the barrier the storing thread also makes sure that the buffer the NEXT chunk
+        // will use is free: the TMA store issued kCBufs - 1 chunks ago has finished reading it.
+        fence_async_smem();
+        if (te == 0) {
+          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCBufs - 2) : "memory");
+          if (has_res && cc + 1 >= kCBufs) mbar_arrive(&cfree_bar[(cc + 1) % kCBufs]);
         }
-      }
-      // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-
-      if (e.row_stats != nullptr && row < g.M) {
-        atomicAdd(e.row_stats + 2 * (size_t)row, rs_sum);
-        atomicAdd(e.row_stats + 2 * (size_t)row + 1, rs_sq);
-      }
-      if (e.gap != nullptr) {
-        // column sums of the staged bf16 tile, split at image boundaries: thread -> (2 columns, 16 rows)
-        const int cpair = te & 31, rq = te >> 5;
-        for (int j = 0; j < C::kCBufs; ++j) {
+        epi_bar_sync();
+        if (te == 0 && e.out_bf16 != nullptr) {
+          tma_store_2d(&tmC, cbase, n0 + j * 64, m0);
+          tma_store_commit();
+        }
+        if (e.gap != nullptr) {
+          // column sums of the staged bf16 chunk, split at image boundaries: thread -> (2 columns, 16 rows)
+          const int cpair = te & 31, rq = te >> 5;
           const int n = n0 + j * 64 + cpair * 2;
-          if (n0 + j * 64 >= g.N) break;
-          if (n >= g.N) continue;
-          const uint8_t* cb = cbuf + j * kCBufBytes;
-          int rr = rq * 16;
-          int img = (m0 + rr) / e.gap_rows;
-          int next = (img + 1) * e.gap_rows - m0;  // first tile row of the next image
-          float s0 = 0.0f, s1 = 0.0f;
-          for (int k = 0; k < 16; ++k, ++rr) {
-            if (m0 + rr >= g.M) break;
-            if (rr == next) {
-              atomicAdd(e.gap + (size_t)img * g.N + n, s0);
-              atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
-              s0 = s1 = 0.0f;
-              ++img;
-              next += e.gap_rows;
+          if (n < g.N && m0 + rq * 16 < g.M) {
+            int rr = rq * 16;
+            int img = (m0 + rr) / e.gap_rows;
+            int next = (img + 1) * e.gap_rows - m0;  // first tile row of the next image
+            float s0 = 0.0f, s1 = 0.0f;
+            for (int k = 0; k < 16; ++k, ++rr) {
+              if (m0 + rr >= g.M) break;
+              if (rr == next) {
+                atomicAdd(e.gap + (size_t)img * g.N + n, s0);
+                atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
+                s0 = s1 = 0.0f;
+                ++img;
+                next += e.gap_rows;
+              }
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(
+                  cbase + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) + (cpair & 3) * 4);
+              s0 += __uint_as_float(w << 16);
+              s1 += __uint_as_float(w & 0xffff0000u);
             }
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(cb + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) +
-                                                                  (cpair & 3) * 4);
-            s0 += __uint_as_float(w << 16);
-            s1 += __uint_as_float(w & 0xffff0000u);
-          }
-          if (m0 + rq * 16 < g.M) {
             atomicAdd(e.gap + (size_t)img * g.N + n, s0);
             atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
           }
         }
       }
-      if (e.gap != nullptr && has_res) epi_bar_sync();  // every thread is done reading the staged tile
-      // staging buffers may be rewritten (by the next residual load or the next tile's epilogue) only after the
-      // TMA stores have finished reading them
-      if (te == 0) {
-        tma_store_wait_read();
-        if (has_res) mbar_arrive(cfree_bar);
+      if (e.row_stats != nullptr && row < g.M) {
+        atomicAdd(e.row_stats + 2 * (size_t)row, rs_sum);
+        atomicAdd(e.row_stats + 2 * (size_t)row + 1, rs_sq);
       }
-      epi_bar_sync();
     }
     if (te == 0) tma_store_wait_all();
   }
@@ -498,39 +591,61 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
+int ensure_neutral(cudaStream_t st) {
+  static bool done = false;  // per process (one device per process in this library's use)
+  if (!done) {
+    init_neutral_kernel<<<8, 256, 0, st>>>();
+    VIP_CUDA(cudaGetLastError());
+    done = true;
+  }
+  return VIP_OK;
+}
+
+template <int BN, bool kDeep>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
            const GemmArgs& g, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN>;
+  using C = Cfg<BN, kDeep>;
+  auto kern = gemm_tcgen05_kernel<BN, kDeep>;
   static bool configured = false;  // per-process; attribute is per-function
   if (!configured) {
-    VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+    VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     configured = true;
   }
   const int tiles = g.m_tiles * g.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
+  const int slots = num_sms() * C::kMinBlocks;
+  const int grid = tiles < slots ? tiles : slots;
+  kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
   VIP_CUDA(cudaGetLastError());
   count_launch();
   return VIP_OK;
 }
 
-// tile width: trade column padding, wave quantisation over the SMs and per-tile efficiency
-int pick_bn(long long M, int N) {
-  const int sms = num_sms();
+// tile width: trade column padding, wave quantisation over the resident CTAs and per-tile efficiency
+int pick_bn(long long M, int N, bool deep) {
+  const int slots = num_sms() * (deep ? 1 : 2);
   const long long mt = (M + BM - 1) / BM;
   int best = 64;
   double best_score = -1.0;
   for (int bn : {256, 128, 64}) {
+    if (!deep && bn == 256) continue;
     const int nt = (N + bn - 1) / bn;
     const long long tiles = mt * nt;
     const double col_eff = (double)N / ((double)nt * bn);
-    const double waves = (double)((tiles + sms - 1) / sms);
-    const double wave_eff = (double)tiles / (waves * sms);
+    const double waves = (double)((tiles + slots - 1) / slots);
+    const double wave_eff = (double)tiles / (waves * slots);
     const double score = col_eff * wave_eff * (bn == 256 ? 1.0 : bn == 128 ? 0.97 : 0.88);
     if (score > best_score) { best_score = score; best = bn; }
   }
   return best;
+}
+
+int pick_mode(const GemmEpilogue& e) {
+  if (e.out_bf16 == nullptr || e.colscale != nullptr || e.act == ACT_SIGMOID) return EPI_GENERIC;
+  const bool ln = e.ln_stats != nullptr, res = e.residual != nullptr;
+  if (res) return (!ln && e.act == ACT_NONE) ? EPI_RES : EPI_GENERIC;
+  if (e.row_stats != nullptr) return EPI_GENERIC;
+  if (ln) return e.act == ACT_NONE ? EPI_LN : e.act == ACT_GELU ? EPI_LN_GELU : EPI_GENERIC;
+  return e.act == ACT_NONE ? EPI_NONE : e.act == ACT_RELU ? EPI_RELU : EPI_GELU;
 }
 
 int check_epilogue(const GemmEpilogue& epi, int N) {
@@ -552,7 +667,11 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
 
 int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, int N, int K, GemmArgs& g,
         const GemmEpilogue& epi, cudaStream_t stream) {
-  const int bn = pick_bn(M, N);
+  VIP_REQUIRE(N <= kMaxCols, VIP_ERR_UNSUPPORTED, "gemm: N = %d exceeds %d", N, kMaxCols);
+  int rc0 = ensure_neutral(stream);
+  if (rc0 != VIP_OK) return rc0;
+  const bool deep = g.num_kb > 4;  // K > 256: the MMA loop dominates; otherwise the epilogue does
+  const int bn = pick_bn(M, N, deep);
   CUtensorMap tmB, tmC, tmR;
   int rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
   if (rc != VIP_OK) return rc;
@@ -566,17 +685,22 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
     rc = make_tmap_2d(&tmR, epi.residual, M, N, epi.ldr, BM);
     if (rc != VIP_OK) return rc;
   }
+  g.mode = pick_mode(epi);
   g.M = (int)M;
   g.N = N;
   g.K = K;
   g.m_tiles = (int)((M + BM - 1) / BM);
   g.n_tiles = (N + bn - 1) / bn;
   g.epi = epi;
-  switch (bn) {
-    case 256: return launch<256>(tmA, tmB, tmC, tmR, g, stream);
-    case 128: return launch<128>(tmA, tmB, tmC, tmR, g, stream);
-    default: return launch<64>(tmA, tmB, tmC, tmR, g, stream);
+  if (deep) {
+    switch (bn) {
+      case 256: return launch<256, true>(tmA, tmB, tmC, tmR, g, stream);
+      case 128: return launch<128, true>(tmA, tmB, tmC, tmR, g, stream);
+      default: return launch<64, true>(tmA, tmB, tmC, tmR, g, stream);
+    }
   }
+  if (bn == 128) return launch<128, false>(tmA, tmB, tmC, tmR, g, stream);
+  return launch<64, false>(tmA, tmB, tmC, tmR, g, stream);
 }
 
 }  // namespace

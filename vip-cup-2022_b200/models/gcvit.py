@@ -73,6 +73,16 @@ class GCViT:
         k = k.reshape(-1, k.shape[-1])
         return self._bf(k.T), (self._f32(W[name + "/bias"]) if bias else None)
 
+    def _dense_scaled(self, W, name, scale_name):
+        """Dense followed by the layer-scale gamma (block.py:41-56,79-80), folded into the weights: g * (x W + b)."""
+        k = np.asarray(W[name + "/kernel"], np.float32)
+        k = k.reshape(-1, k.shape[-1])
+        b = np.asarray(W[name + "/bias"], np.float32)
+        if scale_name in W:
+            g = np.asarray(W[scale_name], np.float32)
+            k, b = k * g[None, :], b * g
+        return self._bf(k.T), self._f32(b)
+
     def _dense_ln(self, W, name, norm):
         """Dense preceded by LayerNormalization ``norm``, packed for the folded-LN contraction (vip_epilogue_t.ln_stats):
         LN(x) W + b = rstd (x (gamma W) - mean colsum(gamma W)) + (beta W + b).  Returns (weights bf16 [out,in], bias',
@@ -184,11 +194,11 @@ class GCViT:
                 p[f"b{i}_{j}"] = dict(
                     n1=(self._f32(W[n + "/norm1/gamma"]), self._f32(W[n + "/norm1/beta"])),
                     n2=(self._f32(W[n + "/norm2/gamma"]), self._f32(W[n + "/norm2/beta"])),
-                    qkv=self._dense_ln(W, n + "/attn/qkv", n + "/norm1"), proj=self._dense(W, n + "/attn/proj"),
-                    fc1=self._dense_ln(W, n + "/mlp/fc1", n + "/norm2"), fc2=self._dense(W, n + "/mlp/fc2"),
-                    rel=self._f32(table),
-                    g1=self._f32(W[n + "/gamma1"]) if n + "/gamma1" in W else None,
-                    g2=self._f32(W[n + "/gamma2"]) if n + "/gamma2" in W else None)
+                    qkv=self._dense_ln(W, n + "/attn/qkv", n + "/norm1"),
+                    proj=self._dense_scaled(W, n + "/attn/proj", n + "/gamma1"),
+                    fc1=self._dense_ln(W, n + "/mlp/fc1", n + "/norm2"),
+                    fc2=self._dense_scaled(W, n + "/mlp/fc2", n + "/gamma2"),
+                    rel=self._f32(table))
             if i < 3:
                 p[f"down{i}"] = self._reduce(W, f"levels/{i}/downsample")
         p["norm"] = (self._f32(W["norm/gamma"]), self._f32(W["norm/beta"]))
@@ -221,10 +231,10 @@ class GCViT:
         wq, bq, cq = d["qkv"]
         qkv = nn.gemm(x2, wq, bias=bq, ln_stats=stats, ln_colsum=cq, ln_cols=c, ln_eps=LN_EPS)
         a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
-        x2 = nn.gemm(a, *d["proj"], colscale=d["g1"], residual=x2, row_stats=st_mid)
+        x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=st_mid)
         w1, b1, c1 = d["fc1"]
         hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
-        x2 = nn.gemm(hdn, *d["fc2"], colscale=d["g2"], residual=x2, row_stats=st_out)
+        x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out)
         return x2.view(b, h, w, c)
 
     def features(self, x, taps=None):
