@@ -27,7 +27,16 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
 }
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// x * Phi(x) with Phi through a fitted tanh form, |error| <= 3e-4 |x| (see gelu_fast in gemm.cu for the derivation)
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  float p = fmaf(-0.00035307545f, x2, 0.037015257f);
+  p = fmaf(p, x2, 0.79749725f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(p * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
 inline int grid_for(long long work, int block) {
   long long g = (work + block - 1) / block;
@@ -57,7 +66,45 @@ __global__ void im2col_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict_
     *reinterpret_cast<uint4*>(out + m * Kp + (long long)tap * C + c8 * 8) = v;
   }
 }
-// generic (any C, e.g. the 3-channel network input); also zero-fills the K..Kp tail
+// generic (any C, e.g. the 3-channel network input); also zero-fills the K..Kp tail.  One thread builds one whole row
+// of the matrix (Kp <= 64) in registers and writes it with 16-byte stores.
+template <int KP, int KS, int CI>
+__global__ void im2col_row_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int stride,
+                                  int pad, int Ho, int Wo) {
+  static_assert(KS * KS * CI <= KP && KP % 8 == 0, "row does not fit");
+  const long long total = (long long)N * Ho * Wo;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(m % Wo);
+    const long long t = m / Wo;
+    const int oy = (int)(t % Ho), n = (int)(t / Ho);
+    unsigned short v[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v[k] = 0;
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const int iy = oy * stride - pad + r;
+#pragma unroll
+      for (int sx = 0; sx < KS; ++sx) {
+        const int ix = ox * stride - pad + sx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const unsigned short* px = reinterpret_cast<const unsigned short*>(x) + (((long long)n * H + iy) * W + ix) * CI;
+#pragma unroll
+          for (int c = 0; c < CI; ++c) v[(r * KS + sx) * CI + c] = __ldg(px + c);
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + m * KP);
+#pragma unroll
+    for (int q = 0; q < KP / 8; ++q) {
+      uint4 u;
+      u.x = v[q * 8 + 0] | ((unsigned)v[q * 8 + 1] << 16);
+      u.y = v[q * 8 + 2] | ((unsigned)v[q * 8 + 3] << 16);
+      u.z = v[q * 8 + 4] | ((unsigned)v[q * 8 + 5] << 16);
+      u.w = v[q * 8 + 6] | ((unsigned)v[q * 8 + 7] << 16);
+      op[q] = u;
+    }
+  }
+}
 __global__ void im2col_scalar_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int ks,
                                      int stride, int pad, int Ho, int Wo, int Kp) {
   const long long total = (long long)N * Ho * Wo * Kp;
@@ -173,21 +220,27 @@ __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __
   }
 }
 
-// ---- LayerNormalization(axis=-1, eps) over [M, C] (block.py:28,39; feature.py:100-101; gcvit.py:79): warp per token
+// ---- LayerNormalization(axis=-1, eps) over [M, C] (block.py:28,39; feature.py:100-101; gcvit.py:79).  A row is handled
+// by LPR lanes (8, 16 or 32, so that narrow rows do not idle most of a warp), J 16-byte chunks per lane.
+template <int LPR, int J>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
                                                         float* __restrict__ row_stats, long long M, int C, float eps) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int c8n = C >> 3;
-  for (long long m = warp0; m < M; m += nwarps) {
-    const bf16* row = x + m * C;
-    float f[4][8];  // up to C = 1024
+  const float invC = 1.0f / (float)C;
+  for (long long m0 = warp0 * RPW; m0 < M; m0 += nwarps * RPW) {
+    const long long m = m0 + rsel;
+    const bool live = m < M;
+    const bf16* row = x + (live ? m : 0) * C;
+    float f[J][8];
     float s = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c8 = lane + 32 * j;
+    for (int j = 0; j < J; ++j) {
+      const int c8 = sub + LPR * j;
       if (c8 < c8n) {
         unpack8(*reinterpret_cast<const bf16x8*>(row + c8 * 8), f[j]);
 #pragma unroll
@@ -195,34 +248,37 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invC;
     float v = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c8 = lane + 32 * j;
+    for (int j = 0; j < J; ++j) {
+      const int c8 = sub + LPR * j;
       if (c8 < c8n) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float d = f[j][k] - mean;
-          v += d * d;
+          v = fmaf(d, d, v);
         }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const float rstd = rsqrtf(v / (float)C + eps);
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = rsqrtf(v * invC + eps);
     float os = 0.0f, oq = 0.0f;  // statistics of the rounded output row (for a LayerNorm folded into the next GEMM)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c8 = lane + 32 * j;
+    for (int j = 0; j < J; ++j) {
+      const int c8 = sub + LPR * j;
       if (c8 < c8n) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8) + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o8[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          o8[k] = (f[j][k] - mean) * rstd * __ldg(gamma + c8 * 8 + k) + __ldg(beta + c8 * 8 + k);
+        for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[j][k] - mean) * rstd, gg[k], bb[k]);
         const bf16x8 pk = pack8(o8);
-        *reinterpret_cast<bf16x8*>(out + m * C + c8 * 8) = pk;
+        if (live) *reinterpret_cast<bf16x8*>(out + m * C + c8 * 8) = pk;
         if (row_stats != nullptr) {
           float r8[8];
           unpack8(pk, r8);
@@ -236,11 +292,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
     }
     if (row_stats != nullptr) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = LPR / 2; o > 0; o >>= 1) {
         os += __shfl_xor_sync(0xffffffffu, os, o);
         oq += __shfl_xor_sync(0xffffffffu, oq, o);
       }
-      if (lane == 0) *reinterpret_cast<float2*>(row_stats + 2 * m) = make_float2(os, oq);
+      if (sub == 0 && live) *reinterpret_cast<float2*>(row_stats + 2 * m) = make_float2(os, oq);
     }
   }
 }
@@ -388,6 +444,9 @@ extern "C" int vip_im2col_bf16(const void* x, int N, int H, int W, int C, int ks
     const long long work = (long long)N * Ho * Wo * ksize * ksize * (C / 8);
     im2col_vec8_kernel<<<grid_for(work, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N, H, W, C, ksize, stride,
                                                                     pad, Ho, Wo, Kp);
+  } else if (Kp == 32 && ksize == 3 && C == 3) {
+    im2col_row_kernel<32, 3, 3><<<grid_for((long long)N * Ho * Wo, 128), 128, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N,
+                                                                                             H, W, stride, pad, Ho, Wo);
   } else {
     const long long work = (long long)N * Ho * Wo * Kp;
     im2col_scalar_kernel<<<grid_for(work, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N, H, W, C, ksize,
@@ -424,7 +483,15 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
                                   long long M, int C, float eps, void* stream) {
   VIP_REQUIRE(x && out && gamma && beta && C % 8 == 0 && C <= 1024, VIP_ERR_INVALID,
               "vip_layernorm_bf16: bad argument (C %% 8 == 0, C <= 1024)");
-  layernorm_kernel<<<grid_for(M * 32, 256), 256, 0, ST(stream)>>>((const bf16*)x, gamma, beta, (bf16*)out, row_stats, M, C, eps);
+  const bf16* xp = (const bf16*)x;
+  bf16* op = (bf16*)out;
+  const int c8n = C / 8;
+  cudaStream_t st = ST(stream);
+  if (c8n <= 8) layernorm_kernel<8, 1><<<grid_for(M * 8, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 16) layernorm_kernel<16, 1><<<grid_for(M * 16, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 32) layernorm_kernel<32, 1><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 64) layernorm_kernel<32, 2><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
+  else layernorm_kernel<32, 4><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
   LAUNCH_CHECK();
 }
 
