@@ -98,6 +98,8 @@ int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, 
  *   row_stats[m] += (sum_n out, sum_n out^2)      if row_stats: feeds the ln_stats of the next contraction (f32 atomics)
  *   gap[m / gap_rows, n] += out                   if gap: GlobalAveragePooling2D partial sums (SE squeeze,
  *        models/resnet_rs/resnet_rs_model.py:149) (f32 atomics)
+ * With row_gate the order is that of an SE bottleneck tail (resnet_rs_model.py:183,278-280):
+ *   v = relu((acc + bias[n]) * row_gate[m / gate_rows, n] + residual[m, n])   (needs residual, act relu, bf16 output)
  * row_stats and gap are accumulated: the caller zeroes them (vip_memset_async). */
 typedef struct vip_epilogue {
   const float* bias;      /* [N] or NULL */
@@ -115,6 +117,8 @@ typedef struct vip_epilogue {
   float* row_stats;       /* [M, 2] or NULL */
   float* gap;             /* [ceil(M / gap_rows), N] or NULL */
   int gap_rows;
+  const float* row_gate;  /* f32 [ceil(M / gate_rows), N] or NULL: squeeze-excite gate of the image a row belongs to */
+  int gate_rows;
 } vip_epilogue_t;
 
 /* vip_gemm_bf16 with the full epilogue. N, K, lda, ldb, ldc, ldr multiples of 8. */

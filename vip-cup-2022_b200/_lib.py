@@ -20,7 +20,8 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("colscale", C.c_void_p), ("residual", C.c_void_p),
                 ("ldr", C.c_int), ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
                 ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
-                ("row_stats", C.c_void_p), ("gap", C.c_void_p), ("gap_rows", C.c_int)]
+                ("row_stats", C.c_void_p), ("gap", C.c_void_p), ("gap_rows", C.c_int),
+                ("row_gate", C.c_void_p), ("gate_rows", C.c_int)]
 
 
 _lib = None

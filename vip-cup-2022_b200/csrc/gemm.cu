@@ -194,14 +194,15 @@ __device__ __forceinline__ void epi_group(float (&v)[8], float rstd, float nmr, 
 
 // Specialised epilogues (compile-time feature sets) for the combinations the backbones use; everything else takes the
 // generic path with neutral parameter vectors.
-enum EpiMode : int { EPI_GENERIC = 0, EPI_NONE, EPI_RELU, EPI_GELU, EPI_LN, EPI_LN_GELU, EPI_RES };
+enum EpiMode : int { EPI_GENERIC = 0, EPI_NONE, EPI_RELU, EPI_GELU, EPI_LN, EPI_LN_GELU, EPI_RES, EPI_SE };
 
 // 32 columns of one output row: TMEM registers -> (folded LN) + bias -> activation -> (+ residual, row statistics) ->
 // bf16 -> swizzled staging row.  `nb` = first column, `cbase16` = 16-byte chunk index of that column inside the row.
 template <int MODE>
 __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
                                           int N, float rstd, float nmr, const float* __restrict__ colsum,
-                                          const float* __restrict__ bias, float& rs_sum, float& rs_sq) {
+                                          const float* __restrict__ bias, float& rs_sum, float& rs_sq,
+                                          const float* __restrict__ gate_row = nullptr) {
   constexpr bool kLN = MODE == EPI_LN || MODE == EPI_LN_GELU;
   constexpr bool kGelu = MODE == EPI_GELU || MODE == EPI_LN_GELU;
 #pragma unroll
@@ -226,6 +227,18 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
       v[i] = t;
     }
     uint4* cp = reinterpret_cast<uint4*>(crow + ((cbase16 + q8) ^ swz) * 16);
+    if (MODE == EPI_SE) {
+      // excite, add the shortcut, ReLU (resnet_rs_model.py:183,278-280)
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + n)), g1 = __ldg(reinterpret_cast<const float4*>(gate_row + n) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const uint4 u = *cp;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        v[2 * t] = fmaxf(fmaf(v[2 * t], gg[2 * t], __uint_as_float(w[t] << 16)), 0.0f);
+        v[2 * t + 1] = fmaxf(fmaf(v[2 * t + 1], gg[2 * t + 1], __uint_as_float(w[t] & 0xffff0000u)), 0.0f);
+      }
+    }
     if (MODE == EPI_RES) {
       const uint4 u = *cp;
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -432,6 +445,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             case EPI_GELU: epi_row32<EPI_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_SE:
+              epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq,
+                                e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N);
+              break;
             default: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
           }
         } else
@@ -621,7 +638,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
 }
 
 // tile width: trade column padding, wave quantisation over the resident CTAs and per-tile efficiency
-int pick_bn(long long M, int N, bool deep) {
+int pick_bn(long long M, int N, bool deep, bool conv) {
   const int slots = num_sms() * (deep ? 1 : 2);
   const long long mt = (M + BM - 1) / BM;
   int best = 64;
@@ -633,13 +650,17 @@ int pick_bn(long long M, int N, bool deep) {
     const double col_eff = (double)N / ((double)nt * bn);
     const double waves = (double)((tiles + slots - 1) / slots);
     const double wave_eff = (double)tiles / (waves * slots);
-    const double score = col_eff * wave_eff * (bn == 256 ? 1.0 : bn == 128 ? 0.97 : 0.88);
+    // im2col-mode TMA delivers an A k-block in ~650 cycles whatever the tile width, so a convolution tile costs the
+    // same time at every BN: prefer the widest one
+    const double tile_eff = conv ? (bn == 256 ? 1.0 : bn == 128 ? 0.55 : 0.3) : (bn == 256 ? 1.0 : bn == 128 ? 0.97 : 0.88);
+    const double score = col_eff * wave_eff * tile_eff;
     if (score > best_score) { best_score = score; best = bn; }
   }
   return best;
 }
 
 int pick_mode(const GemmEpilogue& e) {
+  if (e.row_gate != nullptr) return EPI_SE;
   if (e.out_bf16 == nullptr || e.colscale != nullptr || e.act == ACT_SIGMOID) return EPI_GENERIC;
   const bool ln = e.ln_stats != nullptr, res = e.residual != nullptr;
   if (res) return (!ln && e.act == ACT_NONE) ? EPI_RES : EPI_GENERIC;
@@ -660,6 +681,10 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
   VIP_REQUIRE((epi.row_stats == nullptr && epi.gap == nullptr) || epi.out_bf16 != nullptr, VIP_ERR_UNSUPPORTED,
               "gemm: row_stats / gap need a bf16 output");
   VIP_REQUIRE(epi.gap == nullptr || epi.gap_rows > 0, VIP_ERR_INVALID, "gemm: gap_rows must be set with gap");
+  VIP_REQUIRE(epi.row_gate == nullptr ||
+                  (epi.gate_rows > 0 && epi.residual != nullptr && epi.act == ACT_RELU && epi.out_bf16 != nullptr &&
+                   epi.ln_stats == nullptr && epi.colscale == nullptr && epi.row_stats == nullptr),
+              VIP_ERR_UNSUPPORTED, "gemm: row_gate needs gate_rows, a residual, act relu and a bf16 output (SE bottleneck tail)");
   const void* outp = epi.out_bf16 ? (const void*)epi.out_bf16 : (const void*)epi.out_f32;
   VIP_REQUIRE(((uintptr_t)outp & 15) == 0, VIP_ERR_INVALID, "gemm: output must be 16-byte aligned");
   return VIP_OK;
@@ -671,7 +696,7 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   int rc0 = ensure_neutral(stream);
   if (rc0 != VIP_OK) return rc0;
   const bool deep = g.num_kb > 4;  // K > 256: the MMA loop dominates; otherwise the epilogue does
-  const int bn = pick_bn(M, N, deep);
+  const int bn = pick_bn(M, N, deep, g.conv != 0);
   CUtensorMap tmB, tmC, tmR;
   int rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
   if (rc != VIP_OK) return rc;
@@ -773,6 +798,8 @@ vip::GemmEpilogue to_epilogue(const vip_epilogue_t* p) {
   e.row_stats = p->row_stats;
   e.gap = p->gap;
   e.gap_rows = p->gap_rows;
+  e.row_gate = p->row_gate;
+  e.gate_rows = p->gate_rows;
   return e;
 }
 }  // namespace

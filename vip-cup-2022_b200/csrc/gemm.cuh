@@ -36,6 +36,9 @@ struct GemmEpilogue {
   float* row_stats = nullptr;               // [M, 2] accumulated with atomics; the caller zeroes it
   float* gap = nullptr;                     // [ceil(M / gap_rows), N] accumulated with atomics; the caller zeroes it
   int gap_rows = 0;
+  // SE bottleneck tail: v = relu((acc + bias[n]) * row_gate[m / gate_rows, n] + residual[m, n])
+  const float* row_gate = nullptr;          // [ceil(M / gate_rows), N]
+  int gate_rows = 0;
 };
 
 struct ConvGeom {

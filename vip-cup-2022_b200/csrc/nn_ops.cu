@@ -301,39 +301,70 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   }
 }
 
-// ---- ZeroPadding2D(1) + DepthwiseConv2D(3, valid, no bias) (+ exact GELU) (feature.py:92-94,132-134)
-__global__ void dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[3][3][C]*/,
-                                 bf16* __restrict__ out, int N, int H, int W, int C, int gelu) {
+// ---- ZeroPadding2D(1) + DepthwiseConv2D(3, valid, no bias) (+ GELU) (feature.py:92-94,132-134).  A thread owns one
+// (image, column, 8-channel group) and walks down the rows with the 3x3 window and the 72 weights in registers, so every
+// input element is fetched three times (once per neighbouring column) instead of nine.
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[3][3][C]*/,
+                                                        bf16* __restrict__ out, int N, int H, int W, int C, int gelu) {
   const int c8n = C >> 3;
-  const long long total = (long long)N * H * W * c8n;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % c8n);
-    long long t = i / c8n;
-    const int ox = (int)(t % W);
-    t /= W;
-    const int oy = (int)(t % H), n = (int)(t / H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long total = (long long)N * W * c8n;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  const long long t = idx / c8n;
+  const int ox = (int)(t % W), n = (int)(t / W);
+  float wt[9][8];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = oy - 1 + r;
-      if (iy < 0 || iy >= H) continue;
+  for (int k = 0; k < 9; ++k) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + k * C + c8 * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + k * C + c8 * 8) + 1);
+    wt[k][0] = w0.x; wt[k][1] = w0.y; wt[k][2] = w0.z; wt[k][3] = w0.w;
+    wt[k][4] = w1.x; wt[k][5] = w1.y; wt[k][6] = w1.z; wt[k][7] = w1.w;
+  }
+  const bf16* img = x + (long long)n * H * W * C + c8 * 8;
+  const bool has_l = ox > 0, has_r = ox + 1 < W;
+  float win[3][3][8];  // [row y-1, y, y+1][col x-1, x, x+1]
+  auto load_row = [&](int y, float (&dst)[3][8]) {
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = ox - 1 + s;
-        if (ix < 0 || ix >= W) continue;
-        float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * H + iy) * W + ix) * C + c8 * 8), f);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (r * 3 + s) * C + c8 * 8));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (r * 3 + s) * C + c8 * 8) + 1);
-        acc[0] += f[0] * w0.x; acc[1] += f[1] * w0.y; acc[2] += f[2] * w0.z; acc[3] += f[3] * w0.w;
-        acc[4] += f[4] * w1.x; acc[5] += f[5] * w1.y; acc[6] += f[6] * w1.z; acc[7] += f[7] * w1.w;
+    for (int dx = 0; dx < 3; ++dx) {
+      const bool ok = y >= 0 && y < H && (dx == 1 || (dx == 0 ? has_l : has_r));
+      if (ok) {
+        unpack8(*reinterpret_cast<const bf16x8*>(img + ((long long)y * W + ox - 1 + dx) * C), dst[dx]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[dx][k] = 0.0f;
       }
     }
+  };
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) win[0][dx][k] = 0.0f;
+  load_row(0, win[1]);
+  bf16* op = out + (long long)n * H * W * C + (long long)ox * C + c8 * 8;
+  for (int y = 0; y < H; ++y) {
+    load_row(y + 1, win[2]);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(win[r][sx][k], wt[r * 3 + sx][k], acc[k]);
     if (gelu) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = gelu_erf(acc[k]);
     }
-    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(acc);
+    *reinterpret_cast<bf16x8*>(op + (long long)y * W * C) = pack8(acc);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        win[0][dx][k] = win[1][dx][k];
+        win[1][dx][k] = win[2][dx][k];
+      }
   }
 }
 
@@ -498,8 +529,8 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
 extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, int W, int C, int gelu,
                                   void* stream) {
   VIP_REQUIRE(x && out && w && C % 8 == 0, VIP_ERR_INVALID, "vip_dwconv3x3_bf16: bad argument");
-  dwconv3x3_kernel<<<grid_for((long long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, w, (bf16*)out, N,
-                                                                                         H, W, C, gelu);
+  const long long threads = (long long)N * W * (C / 8);
+  dwconv3x3_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ST(stream)>>>((const bf16*)x, w, (bf16*)out, N, H, W, C, gelu);
   LAUNCH_CHECK();
 }
 

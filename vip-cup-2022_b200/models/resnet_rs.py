@@ -49,6 +49,23 @@ def _dense(W, name, device):
             torch.from_numpy(np.asarray(W[name + "/bias"], np.float32)).to(device).contiguous())
 
 
+def _se_reduce_on_conv2(W, n, device):
+    """The SE squeeze of a bottleneck pools the conv_3 + BN output (resnet_rs_model.py:149,253-262).  conv_3 is 1x1 and BN is
+    affine at inference, so GAP(BN(conv_3(y2))) = W3' mean(y2) + b3': the gate can be computed from the pooled conv_2
+    output BEFORE conv_3 runs and applied inside conv_3's epilogue.  Returns se_reduce composed with that affine map:
+    bf16 [f, f] weights and f32 bias acting on mean(y2)."""
+    k3 = np.asarray(W[n + "conv_3/kernel"], np.float64)[0, 0]                      # (f, 4f)
+    g, b = np.asarray(W[n + "batch_norm_3/gamma"], np.float64), np.asarray(W[n + "batch_norm_3/beta"], np.float64)
+    m, v = np.asarray(W[n + "batch_norm_3/moving_mean"], np.float64), np.asarray(W[n + "batch_norm_3/moving_variance"], np.float64)
+    s = g / np.sqrt(v + BN_EPS)
+    w3, b3 = k3 * s[None, :], b - m * s                                             # y3 = y2 @ w3 + b3
+    k1 = np.asarray(W[n + "se_reduce/kernel"], np.float64)[0, 0]                    # (4f, f)
+    wc = w3 @ k1                                                                    # (f, f): mean(y2) -> hidden pre-activation
+    bc = b3 @ k1 + np.asarray(W[n + "se_reduce/bias"], np.float64)
+    return (torch.from_numpy(np.ascontiguousarray(wc.T.astype(np.float32))).to(device).to(torch.bfloat16).contiguous(),
+            torch.from_numpy(bc.astype(np.float32)).to(device).contiguous())
+
+
 class ResNetRS:
     def __init__(self, depth=50, input_shape=(200, 200, 3), classes=2, classifier_activation="softmax", first_strides=2,
                  device="cuda"):
@@ -115,7 +132,7 @@ class ResNetRS:
                     p[n + "proj"] = _fold_conv_bn(W, n + "projection_conv", n + "projection_batch_norm", d)
                 for j in (1, 2, 3):
                     p[n + f"conv{j}"] = _fold_conv_bn(W, n + f"conv_{j}", n + f"batch_norm_{j}", d)
-                p[n + "se1"] = _dense(W, n + "se_reduce", d)
+                p[n + "se1"] = _se_reduce_on_conv2(W, n, d)
                 p[n + "se2"] = _dense(W, n + "se_expand", d)
         p["head_w"] = torch.from_numpy(np.asarray(W["predictions/kernel"], np.float32)).to(d).contiguous()
         p["head_b"] = torch.from_numpy(np.asarray(W["predictions/bias"], np.float32)).to(d).contiguous()
@@ -129,15 +146,14 @@ class ResNetRS:
             s_in = nn.avgpool2_same(x) if strides == 2 else x
             shortcut = nn.conv2d(s_in, *p[n + "proj"])
         y = nn.conv2d(x, *p[n + "conv1"], act="relu")
-        y = nn.conv2d(y, *p[n + "conv2"], ksize=3, stride=strides, pad=1, act="relu")
-        # conv3 + folded BN; the SE squeeze (GlobalAveragePooling2D, resnet_rs_model.py:149) is accumulated by the
-        # GEMM epilogue, so the 4f-channel map is not read again before the excite pass
-        b, h, w, _ = y.shape
-        y = nn.conv2d(y, *p[n + "conv3"], gap=gap, gap_rows=h * w)
+        # conv_2 + BN + ReLU; its epilogue also accumulates the per-image channel sums the SE gate needs
+        y = nn.conv2d(y, *p[n + "conv2"], ksize=3, stride=strides, pad=1, act="relu", gap=gap, gap_rows=None)
+        b, h, w, f = y.shape
         pooled = nn.scale_cast_bf16(gap, 1.0 / (h * w))
         hid = nn.gemm(pooled, *p[n + "se1"], act="relu")
         gate = nn.gemm(hid, *p[n + "se2"], act="sigmoid", out_dtype=torch.float32)
-        return nn.scale_add_act(y, gate, shortcut, act="relu", out=y)
+        # conv_3 + BN, excite, + shortcut, ReLU in one epilogue (resnet_rs_model.py:253-280)
+        return nn.conv2d(y, *p[n + "conv3"], act="relu", residual=shortcut, row_gate=gate, gate_rows=h * w)
 
     def features(self, x, taps=None):
         """x bf16 [N,H,W,3] -> bf16 [N,h,w,2048]"""
@@ -150,11 +166,11 @@ class ResNetRS:
             taps["stem"] = x
         nimg = x.shape[0]
         nblocks = sum(r for _, r in BLOCK_ARGS[self.depth])
-        gaps = nn.zero_(torch.empty((nblocks, nimg, 2048), dtype=torch.float32, device=x.device))  # one memset
+        gaps = nn.zero_(torch.empty((nblocks, nimg, 512), dtype=torch.float32, device=x.device))  # one memset
         k = 0
         for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
             for bi in range(reps):
-                gap = gaps[k].view(-1)[: nimg * 4 * f].view(nimg, 4 * f)
+                gap = gaps[k].view(-1)[: nimg * f].view(nimg, f)
                 k += 1
                 x = self._bottleneck(x, f"c{gi + 2}_block_{bi}_", (1 if gi == 0 else 2) if bi == 0 else 1, bi == 0, gap)
             if taps is not None:

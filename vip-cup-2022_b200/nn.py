@@ -27,10 +27,10 @@ def _chk(t, name, dtype=BF16):
 
 
 def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=None, ln_colsum=None, ln_cols=0,
-              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0):
+              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0, row_gate=None, gate_rows=0):
     _chk(residual, "residual")
     for name, t in (("bias", bias), ("colscale", colscale), ("ln_stats", ln_stats), ("ln_colsum", ln_colsum),
-                    ("row_stats", row_stats), ("gap", gap)):
+                    ("row_stats", row_stats), ("gap", gap), ("row_gate", row_gate)):
         _chk(t, name, torch.float32)
     e = _lib.Epilogue()
     e.bias, e.act, e.colscale = _p(bias), ACT[act], _p(colscale)
@@ -39,6 +39,7 @@ def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=N
     e.out_dtype = _lib.VIP_DTYPE_BF16 if out.dtype == BF16 else _lib.VIP_DTYPE_F32
     e.ln_stats, e.ln_colsum, e.ln_cols, e.ln_eps = _p(ln_stats), _p(ln_colsum), int(ln_cols), float(ln_eps)
     e.row_stats, e.gap, e.gap_rows = _p(row_stats), _p(gap), int(gap_rows)
+    e.row_gate, e.gate_rows = _p(row_gate), int(gate_rows)
     return e
 
 
@@ -68,6 +69,8 @@ def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, *
     ho = (h + 2 * pad - ksize) // stride + 1
     wo = (wd + 2 * pad - ksize) // stride + 1
     cout = w.shape[0]
+    if fused.get("gap") is not None and not fused.get("gap_rows"):
+        fused["gap_rows"] = ho * wo
     res2 = None if residual is None else residual.view(n * ho * wo, -1)
     if ksize == 1 and stride == 1 and pad == 0 and w.shape[1] == c:
         y = gemm(x.view(n * h * wd, c), w, bias=bias, act=act, residual=res2, **fused)
