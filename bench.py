@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json metric on the B200 path, one JSON line on stdout (rank 0).
+"""bench.py -- BASELINE.json metric "images/sec at 200x200 (preprocess+ensemble fwd)" on the B200 path; ONE JSON line on
+stdout (rank 0).
 
-Workload at every N (weak scaling, no data-path collective: images are independent):
-BASELINE.json configs[1] -- the augment pipeline on a 4096-image batch per GPU:
-u8 [4096,200,200,3] -> random crop -> bicubic 224x224 -> /255 -> JPEG q in [65,100) -> flips -> f32 [4096,224,224,3].
-A "step" is one pass of that path over one batch.
+Workload at every N (weak scaling; images are independent, so ranks share nothing on the data path):
+BASELINE.json configs[3] -- 1024 decoded 200x200 uint8 images per GPU per step -> fused preprocessing (identity resize for
+ResNet-RS-101 @200, bicubic 200->224 for GCViT-small @224, /255, bf16) -> ResNet-RS-101 forward + GCViT-small forward
+(random-init weights) -> softmax heads -> ensemble mean of P(synthetic) in float64.  A "step" is one pass of that path over
+one batch; the whole step is one CUDA graph.
 
-  value      images/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the host-buffer C-ABI call (pinned host in/out, H2D + D2H inside the timed region)
-  roofline   dominant kernel (preprocess_kernel): algorithmic bytes (722 112 B/image) / CUDA-event time / measured HBM peak
-  cpu_baseline  the numpy oracle (oracle/preprocess.py) timed on this box's host cores (rank 0, N=1 only)
+  value         images/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e           same path through EnsemblePredictor.predict_host: pinned host uint8 in, H2D + graph + D2H of the [B]
+                probabilities inside the timed region
+  roofline      tensor-bound: algorithmic FLOPs of the step (31.06 GFLOP/image) / CUDA-event step time /
+                measured sustained bf16 peak; the tcgen05 GEMM / implicit-conv kernel is the dominant kernel
+  preprocess_only  BASELINE.json configs[1] (augment pipeline on a 4096-image batch, HBM-bound declaration) with its own
+                roofline object -- the kernel `roofline.traffic` was captured for
+  cpu_baseline  the CPU oracle (oracle/: numpy preprocessing + PyTorch-CPU fp32 backbones) on a bounded sample (rank 0, N=1)
 
-``--impl reference`` times the CPU restatement of the reference path on all host cores (the TensorFlow reference
-itself cannot be installed offline) and prints the same line with "impl": "reference".
+``--impl reference`` times the CPU restatement of the reference path on all host cores (the TensorFlow reference itself
+cannot be installed offline) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -26,21 +32,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_IMAGES = 4096
+BATCH = 1024                      # images per GPU per step (configs[3])
 HS = WS = 200
-HO = WO = 224
-BYTES_PER_IMAGE = HS * WS * 3 + HO * WO * 3 * 4  # 722 112 algorithmic bytes
+MODELS = [("ResNetRS101-200x200", (200, 200)), ("GCViTSmall-224x224", (224, 224))]
+GFLOP_PER_IMAGE = 14.00 + 17.06
 METRIC = "images/sec at 200x200 (preprocess+ensemble fwd)"
-WORKLOAD = "configs[1]: augment pipeline (crop->bicubic 200->224->/255->JPEG q[65,100)->flip), 4096-image batch per GPU"
+WORKLOAD = ("configs[3]: 1024 decoded 200x200 u8 images per GPU -> fused preprocess (200 and 224) -> ResNet-RS-101 + "
+            "GCViT-small forward (random-init, bf16) -> softmax heads -> float64 ensemble mean")
+PRE_N, PRE_HO = 4096, 224
+PRE_BYTES_PER_IMAGE = HS * WS * 3 + PRE_HO * PRE_HO * 3 * 4  # 722 112 algorithmic bytes
 
 
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 def _traffic():
@@ -107,34 +116,42 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def _cpu_one(args):
+# ---- CPU legs (the only places that touch oracle/) ---------------------------------------------------------------
+_ORACLE_W = {}
+
+
+def _oracle_step(n_images: int, threads: int):
+    """One pass of the same path on the CPU oracle over ``n_images`` synthetic images.  Returns seconds."""
+    import numpy as np
+    import torch
+
+    from oracle import gcvit as G
     from oracle import preprocess as P
+    from oracle import resnet_rs as R
 
-    i, crop, q, flag, backend = args
-    src = P.synth_image(i % 64, HS, WS)
-    return float(P.preprocess_one(src, HO, WO, crop, q, flag, jpeg_backend=backend).sum())
-
-
-def cpu_baseline(n_sample: int, cores: int, backend: str):
-    """Times the oracle on ``n_sample`` images of the same workload. Returns images/s."""
-    from oracle import preprocess as P
-
-    crops, q, flags = P.synth_decisions(N_IMAGES)
-    jobs = [(i, crops[i], int(q[i]), int(flags[i]), backend) for i in range(n_sample)]
-    for j in jobs[: min(8, n_sample)]:
-        _cpu_one(j)  # warm caches / imports
+    torch.set_num_threads(threads)
+    if not _ORACLE_W:
+        _ORACLE_W["rs"] = R.random_weights(101, 2, seed=0)
+        _ORACLE_W["gc"] = G.random_weights("small", 2, seed=0)
+        _ORACLE_W["img"] = np.stack([P.synth_image(i, HS, WS) for i in range(8)])
+    src = _ORACLE_W["img"][np.arange(n_images) % 8]
     t0 = time.perf_counter()
-    if cores == 1:
-        for j in jobs:
-            _cpu_one(j)
-    else:
-        import multiprocessing as mp
+    x200 = np.stack([P.decode_to_float(im, 200, 200) for im in src])
+    x224 = np.stack([P.decode_to_float(im, 224, 224) for im in src])
+    p1 = R.forward(x200, _ORACLE_W["rs"], 101, head_act="softmax")
+    p2 = G.forward(x224, _ORACLE_W["gc"], "small", head_act="softmax")
+    _ = np.mean([1.0 - p1[:, 0].astype(np.float64), 1.0 - p2[:, 0].astype(np.float64)], axis=0)
+    return time.perf_counter() - t0
 
-        with mp.get_context("fork").Pool(cores) as pool:
-            t0 = time.perf_counter()
-            pool.map(_cpu_one, jobs, chunksize=max(1, n_sample // (cores * 4)))
-    dt = time.perf_counter() - t0
-    return n_sample / dt
+
+def cpu_baseline(threads: int, budget_s: float = 20.0):
+    """Oracle throughput on a bounded sample (about ``budget_s`` of CPU work).  Returns (images/s, sample description)."""
+    n0 = 2
+    t = _oracle_step(n0, threads)          # warm-up + calibration (includes weight generation the first time)
+    t = _oracle_step(n0, threads)
+    n = int(max(2, min(64, budget_s / max(t / n0, 1e-3))))
+    t = _oracle_step(n, threads)
+    return n / t, f"{n} images of the 1024-image batch (after a 2-image warm-up), {threads} torch threads"
 
 
 def run_reference(args):
@@ -142,21 +159,25 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    sample = 64 * max(1, min(cores, 32) // 4)  # bounded sample per step
-    vals = []
-    for s in range(args.warmup + args.steps):
-        v = cpu_baseline(sample, cores, "pillow")
+    _oracle_step(2, cores)
+    t2 = _oracle_step(2, cores)
+    total_steps = args.steps + args.warmup
+    n = int(max(2, min(32, 150.0 / max(total_steps, 1) / max(t2 / 2, 1e-3))))   # whole run stays within a few minutes
+    times = []
+    for s in range(total_steps):
+        dt = _oracle_step(n, cores)
         if s >= args.warmup:
-            vals.append(v)
-    value = len(vals) / sum(1.0 / v for v in vals)
+            times.append(dt)
+    value = n * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference path (TensorFlow is not installable "
-                   "offline): numpy bicubic + libjpeg-turbo (Pillow) JPEG round trip, fork pool over all host cores"},
+                   "offline): numpy bicubic + /255, PyTorch-CPU fp32 ResNet-RS-101 + GCViT-small, all host cores; each step "
+                   f"is a bounded sample of {n} images of the batch"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} images of the 4096-image batch per step"},
+                         "sample": f"{n} images per step"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -164,11 +185,45 @@ def run_reference(args):
     return 0
 
 
+# ---- GPU legs -------------------------------------------------------------------------------------------------------
+def bench_preprocess_only(dev, steps):
+    """configs[1]: the augment pipeline alone on a 4096-image batch (crop -> bicubic 224 -> /255 -> JPEG q -> flips)."""
+    import numpy as np
+    import torch
+
+    from vipcup_b200 import ops
+
+    rng = np.random.default_rng(1234)
+    base = rng.integers(0, 256, (64, HS, WS, 3), dtype=np.uint8)
+    base = ((base.astype(np.uint16) + np.roll(base, 1, 2) + np.roll(base, 2, 2) + np.roll(base, 1, 1)) // 4).astype(np.uint8)
+    src = torch.from_numpy(np.tile(base, (PRE_N // 64, 1, 1, 1))).to(dev)
+    side = rng.integers(160, 201, PRE_N)
+    y0 = (rng.random(PRE_N) * (HS - side + 1)).astype(np.int64)
+    x0 = (rng.random(PRE_N) * (WS - side + 1)).astype(np.int64)
+    crops = torch.from_numpy(np.stack([y0, x0, side, side], 1).astype(np.int32)).to(dev)
+    q = torch.from_numpy(rng.integers(65, 100, PRE_N).astype(np.int32)).to(dev)
+    flags = torch.from_numpy((rng.integers(0, 2, PRE_N) + 2 * rng.integers(0, 2, PRE_N)).astype(np.uint8)).to(dev)
+    out = torch.empty((PRE_N, PRE_HO, PRE_HO, 3), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ops.preprocess(src, (PRE_HO, PRE_HO), crops, q, flags, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        ops.preprocess(src, (PRE_HO, PRE_HO), crops, q, flags, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del out, src
+    return ms
+
+
 def run_ours(args):
     import numpy as np
     import torch
 
-    from vipcup_b200 import _lib, ops
+    from vipcup_b200 import _lib, registry
+    from vipcup_b200.predict import EnsemblePredictor
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,93 +238,96 @@ def run_ours(args):
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
 
-    # synthetic inputs (generated with numpy only; the oracle module is not touched on the product path)
+    # models (random-init: checkpoints are unavailable offline) and synthetic decoded images
+    models = []
+    for name, dim in MODELS:
+        models.append((registry.create_model(name, dim, num_classes=2, device=dev).init_random(seed=rank), dim))
     rng = np.random.default_rng(1234 + rank)
     base = rng.integers(0, 256, (64, HS, WS, 3), dtype=np.uint8)
-    # low-pass in x so that JPEG sees natural-ish statistics
     base = ((base.astype(np.uint16) + np.roll(base, 1, 2) + np.roll(base, 2, 2) + np.roll(base, 1, 1)) // 4).astype(np.uint8)
-    src_h = torch.from_numpy(np.tile(base, (N_IMAGES // 64, 1, 1, 1))).pin_memory()
-    side = rng.integers(160, 201, N_IMAGES)
-    y0 = (rng.random(N_IMAGES) * (HS - side + 1)).astype(np.int64)
-    x0 = (rng.random(N_IMAGES) * (WS - side + 1)).astype(np.int64)
-    crops_h = torch.from_numpy(np.stack([y0, x0, side, side], 1).astype(np.int32)).pin_memory()
-    q_h = torch.from_numpy(rng.integers(65, 100, N_IMAGES).astype(np.int32)).pin_memory()
-    flags_h = torch.from_numpy((rng.integers(0, 2, N_IMAGES) + 2 * rng.integers(0, 2, N_IMAGES)).astype(np.uint8)).pin_memory()
-
-    src, crops, q, flags = (t.to(dev) for t in (src_h, crops_h, q_h, flags_h))
-    out = torch.empty((N_IMAGES, HO, WO, 3), dtype=torch.float32, device=dev)
-
-    def step():
-        ops.preprocess(src, (HO, WO), crops, q, flags, out=out)
+    src_h = torch.from_numpy(np.tile(base, (BATCH // 64, 1, 1, 1))).pin_memory()
+    pred = EnsemblePredictor(models, BATCH, (HS, WS), dev)
+    pred.src.copy_(src_h)
+    out_h = torch.empty((BATCH,), dtype=torch.float64).pin_memory()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for _ in range(warmup):
+        pred.run()
     barrier()
     sampler = ClockSampler(local_rank)
-    _lib.launch_count_reset()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     sampler.start()
     barrier()
     evs[0].record()
-    for i in range(args.steps):
-        step()
-        evs[i + 1].record()
+    for _ in range(args.steps):
+        pred.run()
+    evs[1].record()
     barrier()
     clocks = sampler.stop()
-    launches = _lib.launch_count()
-    total_ms = evs[0].elapsed_time(evs[-1])
-    per_kernel_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    kernel_ms = float(np.mean(per_kernel_ms))
+    total_ms = evs[0].elapsed_time(evs[1])
+    finite = bool(torch.isfinite(pred.acc).all())
 
-    # e2e through the host-buffer entry point (pinned host in, pinned host out)
-    out_h = torch.empty((N_IMAGES, HO, WO, 3), dtype=torch.float32).pin_memory()
-    e2e_steps = max(2, min(args.steps, 5))
-    ops.preprocess_host(src_h, (HO, WO), crops_h, q_h, flags_h, out=out_h)
+    # e2e through the host-buffer call: pinned host images in, probabilities out
+    e2e_steps = max(2, min(args.steps, 10))
+    pred.predict_host(src_h, out_h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ops.preprocess_host(src_h, (HO, WO), crops_h, q_h, flags_h, out=out_h)
+        pred.predict_host(src_h, out_h)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, kernel_ms = (float(v) for v in t.tolist())
+    total_ms, e2e_s = (float(v) for v in t.tolist())
 
     if rank == 0:
-        peak, peak_src = _peaks()
-        achieved = BYTES_PER_IMAGE * N_IMAGES / (kernel_ms * 1e-3) / 1e9
+        hbm_peak, tc_peak, peak_src = _peaks()
+        step_ms = total_ms / args.steps
+        achieved_tf = GFLOP_PER_IMAGE * BATCH / step_ms  # GFLOP / ms = TFLOP/s
         line = {
-            "metric": METRIC, "value": world * N_IMAGES * args.steps / (total_ms * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu_per_step": N_IMAGES, "src": [HS, WS], "out": [HO, WO],
-                       "out_dtype": "f32", "l2": "inputs+outputs (2.96 GB/step) larger than the 126 MB L2",
-                       "sharding": "images sharded across ranks, no data-path collective"},
+            "metric": METRIC, "value": world * BATCH * args.steps / (total_ms * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": step_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu_per_step": BATCH, "src": [HS, WS],
+                       "models": [m for m, _ in MODELS], "weights": "random-init (seeded)",
+                       "l2": "activations per step (> 10 GB) far exceed the 126 MB L2",
+                       "sharding": "images sharded across ranks, models replicated, no data-path collective",
+                       "finite_outputs": finite},
             "clocks": clocks,
-            "e2e": {"value": world * N_IMAGES * e2e_steps / e2e_s, "unit": "images/s",
-                    "h2d_bytes_per_step": int(src_h.nbytes + crops_h.nbytes + q_h.nbytes + flags_h.nbytes),
-                    "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps,
-                    "api": "vip_preprocess_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"},
-            "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": _traffic(), "kernel": "preprocess_kernel<f32>", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": BYTES_PER_IMAGE * N_IMAGES,
-                         "avg_launch_ms": kernel_ms,
-                         "note": "JPEG emulation makes the kernel ALU-issue-bound, see DESIGN.md"},
+            "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s",
+                    "h2d_bytes_per_step": int(src_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps,
+                    "api": "EnsemblePredictor.predict_host (pinned host u8 batch -> H2D -> CUDA graph -> D2H [B] f64)"},
+            "gpu_launches": int(pred.launches_per_step or 0) * args.steps * world,
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tc_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / tc_peak, "traffic": None,
+                         "kernel": "gemm_tcgen05_kernel (tcgen05 GEMM / implicit-GEMM conv), whole-step average",
+                         "peak_source": peak_src + ", sustained bf16 figure (kernel timed inside a long step)",
+                         "algorithmic_flops_per_step": GFLOP_PER_IMAGE * 1e9 * BATCH,
+                         "note": "achieved = algorithmic FLOPs of the step / CUDA-event step time (all kernels of the step, "
+                                 "not only the GEMMs); per-kernel shares: profiles/"},
         }
+        if not args.no_preprocess_only:
+            pre_ms = bench_preprocess_only(dev, max(5, min(args.steps, 20)))
+            ach = PRE_BYTES_PER_IMAGE * PRE_N / (pre_ms * 1e-3) / 1e9
+            line["preprocess_only"] = {
+                "workload": "configs[1]: crop -> bicubic 200->224 -> /255 -> JPEG q[65,100) -> flips, 4096 images, f32 out",
+                "value": PRE_N / (pre_ms * 1e-3), "unit": "images/s", "ms_per_launch": pre_ms,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                             "traffic": _traffic(), "kernel": "preprocess_kernel<f32>",
+                             "algorithmic_bytes_per_launch": PRE_BYTES_PER_IMAGE * PRE_N,
+                             "note": "JPEG emulation makes the kernel ALU-issue-bound, see DESIGN.md"}}
         if world == 1 and not args.no_cpu_baseline:
-            n_sample = 256
-            v = cpu_baseline(n_sample, 1, "integer")
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": 1, "kind": "port",
-                                    "sample": f"first {n_sample} images of the batch, numpy oracle, 1 thread"}
+            cores = os.cpu_count() or 1
+            v, sample = cpu_baseline(cores)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -280,10 +338,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-preprocess-only", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

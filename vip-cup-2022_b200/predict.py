@@ -124,3 +124,77 @@ def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None):
                 print("\n> FINAL PREDICTION SAVED TO ", CFG.output_csv_path)
                 print(pred_df.head(2))
     return pred_df
+
+
+class EnsemblePredictor:
+    """Device-side half of the hot path for a fixed batch size: decoded uint8 images -> fused preprocessing (one kernel per
+    distinct model resolution, dataset/dataset.py:31-37) -> every backbone forward -> head with the ensemble mean of
+    P(synthetic) accumulated in float64 by the head kernel (main.py:113-114,142).  The whole sequence is captured in ONE
+    CUDA graph, so a step is: H2D copy of the batch, graph replay, D2H copy of [B] probabilities.
+
+    models: list of (model, (H, W)) already holding their weights.  ``flags`` (uint8 [B] VIP_FLAG_* bits) select the
+    flip / gray test-time augmentation of dataset/augment.py:115-120,142-146."""
+
+    def __init__(self, models, batch, src_hw=(200, 200), device=None, use_graph=True):
+        from . import nn, ops
+
+        self.models, self.batch, self.src_hw = list(models), int(batch), tuple(src_hw)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._nn, self._ops = nn, ops
+        b, (hs, ws) = self.batch, self.src_hw
+        self.src = torch.zeros((b, hs, ws, 3), dtype=torch.uint8, device=self.device)
+        self.flags = torch.zeros((b,), dtype=torch.uint8, device=self.device)
+        self.acc = torch.zeros((b,), dtype=torch.float64, device=self.device)      # ensemble mean of P(synthetic)
+        self.probs = [None] * len(self.models)
+        self.graph = None
+        self.launches_per_step = None
+        if use_graph:
+            self._capture()
+
+    def _step(self):
+        nn, ops = self._nn, self._ops
+        nn.zero_(self.acc)
+        pre = {}
+        w = 1.0 / len(self.models)
+        for i, (model, dim) in enumerate(self.models):
+            dim = tuple(int(v) for v in dim)
+            if dim not in pre:
+                pre[dim] = ops.preprocess(self.src, dim, None, None, self.flags, out_dtype=torch.bfloat16)
+            self.probs[i] = model(pre[dim], acc=self.acc, acc_weight=w)
+
+    def _capture(self):
+        from . import _lib
+
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step()                      # warm-up: lazy kernel attributes, neutral vectors, allocator pools
+            torch.cuda.synchronize(self.device)
+            _lib.launch_count_reset()
+            self._step()
+            self.launches_per_step = _lib.launch_count()
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=s):
+                self._step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+
+    def run(self):
+        """One pass over the batch currently in ``self.src`` / ``self.flags``; results in ``self.acc`` / ``self.probs``."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.acc
+
+    def predict_host(self, src_u8_host, out_host=None, flags_host=None):
+        """Pinned host uint8 [B,Hs,Ws,3] -> pinned host float64 [B] ensemble P(synthetic) (copies on the current stream)."""
+        self.src.copy_(src_u8_host, non_blocking=True)
+        if flags_host is not None:
+            self.flags.copy_(flags_host, non_blocking=True)
+        self.run()
+        if out_host is None:
+            out_host = torch.empty((self.batch,), dtype=torch.float64).pin_memory()
+        out_host.copy_(self.acc, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
