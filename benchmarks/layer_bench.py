@@ -54,11 +54,25 @@ def main():
                               ("ref 8192^3", 8192, 8192, 8192, "")]:
         cases.append((name, "gemm", (m, n, k, ex)))
 
+    for name, h, ws, heads, glob in [("gc.L0.attn ws7 h2 @56", 56, 7, 2, False), ("gc.L1.attn ws7 h4 @28", 28, 7, 4, True),
+                                     ("gc.L2.attn ws14 h8 @14", 14, 14, 8, False), ("gc.L2.attn ws14 h8 glob", 14, 14, 8, True),
+                                     ("gc.L3.attn ws7 h16 @7", 7, 7, 16, False)]:
+        cases.append((name, "attn", (h, ws, heads, glob)))
+
     print(f"{'layer':32s} {'us':>9s} {'GB/s':>8s} {'%hbm':>6s} {'TF/s':>8s} {'%tc':>6s}   bound-by-roofline us")
     for name, kind, prm in cases:
         if args.only and args.only not in name and args.only != kind:
             continue
-        if kind == "conv":
+        if kind == "attn":
+            h, ws, heads, glob = prm
+            c = heads * 32
+            qkv = rnd(B * h * h, (2 if glob else 3) * c) * 5
+            qg = rnd(B, ws * ws, c) * 5 if glob else None
+            table = torch.randn(heads, (2 * ws - 1) ** 2, device=dev)
+            fn = lambda: nn.window_attention(qkv, qg, table, B, h, h, c, ws, heads)
+            flops = 4.0 * B * h * h * ws * ws * c
+            byts = 2.0 * (qkv.numel() + B * h * h * c)
+        elif kind == "conv":
             h, c, co, k, s = prm
             x = rnd(B, h, h, c)
             w = rnd(co, k * k * c)

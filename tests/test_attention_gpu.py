@@ -1,6 +1,7 @@
 """vip_window_attention_bf16 (tensor-core window attention, models/gcvit/layers/attention.py:52-83 with
 window_partition/reverse of layers/window.py:3-14 folded in) against a plain PyTorch fp32 restatement of the same op on
-the same bf16-rounded inputs.  Tolerance: bf16 output rounding + bf16 P operand -> 2e-2 absolute on O(1) values."""
+the same bf16-rounded inputs.  Tolerance: bf16 output rounding (half an ulp = 2^-9 relative) + bf16 P operand ->
+8e-3 x max(1, max |reference|)."""
 import numpy as np
 import pytest
 
@@ -34,9 +35,23 @@ def _ref(qkv, qg, table, B, H, W, C, ws, heads):
     return o
 
 
+@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
 @pytest.mark.parametrize("B,H,ws,heads,glob", [(2, 14, 7, 2, False), (3, 21, 7, 4, True), (2, 14, 14, 8, False),
                                                (1, 14, 14, 3, True), (5, 7, 7, 16, False), (1, 56, 7, 2, True)])
-def test_window_attention_matches_torch(cuda_device, B, H, ws, heads, glob):
+def test_window_attention_matches_torch(cuda_device, B, H, ws, heads, glob, impl):
+    """Both implementations (attention.cu mma.sync, attention_tc.cu tcgen05/TMEM); the library reads VIP_ATTN_TCGEN05
+    once per process, so the tcgen05 kernel is exercised in a child process."""
+    if impl == "tcgen05":
+        import os
+        import subprocess
+        import sys
+
+        if os.environ.get("VIP_ATTN_TCGEN05") != "1":
+            env = dict(os.environ, VIP_ATTN_TCGEN05="1")
+            r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k",
+                                f"tcgen05 and {B}-{H}-{ws}-{heads}-{glob}"], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout[-3000:]
+            return
     import torch
 
     from vipcup_b200 import nn
@@ -52,4 +67,5 @@ def test_window_attention_matches_torch(cuda_device, B, H, ws, heads, glob):
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
     assert torch.isfinite(got).all()
-    assert err < 2e-2, f"max abs err {err}"
+    tol = 8e-3 * max(1.0, ref.abs().max().item())
+    assert err < tol, f"max abs err {err} > {tol}"

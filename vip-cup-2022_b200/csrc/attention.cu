@@ -17,6 +17,7 @@
 //   O       P (bf16 A fragments built from the S accumulators) x V (ldmatrix.trans), / row sum
 //   store   through the (consumed) q rows in shared memory -> coalesced 16-byte stores
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -56,24 +57,33 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 template <int WS>
 struct AttnCfg {
-  static constexpr int N = WS * WS;               // tokens per window
-  static constexpr int KT = (N + 15) / 16;        // 16-key steps of P @ V (= 16-row query tiles)
-  static constexpr int NT = 2 * KT;               // 8-key tiles of S
-  static constexpr int ROWS = KT * 16;            // staged rows per operand (zero padded)
+  static constexpr int N = WS * WS;                 // tokens per window
+  static constexpr int WP = WS <= 8 ? 8 : 16;       // key rows padded to a whole number of 8-key tiles: the window row of
+                                                    // a key tile is then a compile-time constant (cheap bias addressing)
+  static constexpr int KEYS = WS * WP;              // padded keys (56 / 224)
+  static constexpr int KT = (KEYS + 15) / 16;       // 16-key steps of P @ V
+  static constexpr int NT = 2 * KT;                 // 8-key tiles of S
+  static constexpr int KROWS = KT * 16;             // staged key / value rows (zero padded)
+  static constexpr int QT = (N + 15) / 16;          // 16-row query tiles
+  static constexpr int QROWS = QT * 16;
+  static constexpr int NB = WS <= 8 ? 1 : 2;        // key blocks of the online softmax (bounds the S registers)
+  static constexpr int NTB = NT / NB, KTB = KT / NB;
   static constexpr int TAB = (2 * WS - 1) * (2 * WS - 1);
-  static constexpr int kWarpsPerPair = WS <= 7 ? 1 : 4;
+  static constexpr int TPAD = 4;                    // padded keys index up to 2 entries before the table
+  static constexpr int kWarpsPerPair = WS <= 8 ? 1 : 4;
   static constexpr int kPairsPerCta = 4 / kWarpsPerPair;
-  static constexpr int kPairBytes = 3 * ROWS * PITCH * 2 + ((TAB * 4 + 15) / 16) * 16;
+  static constexpr int kPairBytes = (QROWS + 2 * KROWS) * PITCH * 2 + (((TAB + TPAD) * 4 + 15) / 16) * 16;
   static constexpr int kSmem = kPairsPerCta * kPairBytes;
+  static_assert(NT % NB == 0 && KT % NB == 0, "key blocks must split evenly");
 };
 
 template <int WS>
-__global__ void __launch_bounds__(128) window_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ qg,
-                                                                   const float* __restrict__ table /*[heads][TAB]*/,
-                                                                   bf16* __restrict__ out, int H, int W, int C, int heads,
-                                                                   int num_pairs, float scale_log2e) {
+__global__ void __launch_bounds__(128, WS <= 8 ? 3 : 4)
+window_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ qg, const float* __restrict__ table /*[heads][TAB]*/,
+                            bf16* __restrict__ out, int H, int W, int C, int heads, int num_pairs, float scale_log2e) {
   using Cfg = AttnCfg<WS>;
-  constexpr int N = Cfg::N, KT = Cfg::KT, NT = Cfg::NT, ROWS = Cfg::ROWS, TAB = Cfg::TAB;
+  constexpr int N = Cfg::N, WP = Cfg::WP, KT = Cfg::KT, KROWS = Cfg::KROWS, QT = Cfg::QT, QROWS = Cfg::QROWS;
+  constexpr int NB = Cfg::NB, NTB = Cfg::NTB, KTB = Cfg::KTB, TAB = Cfg::TAB, TPAD = Cfg::TPAD;
   constexpr int WPP = Cfg::kWarpsPerPair;
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,23 +103,31 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const bf16* _
   const int koff = (global_q ? 0 : C) + h * HD, voff = koff + C;
 
   bf16* sQ = reinterpret_cast<bf16*>(smem + pair_in_cta * Cfg::kPairBytes);
-  bf16* sK = sQ + ROWS * PITCH;
-  bf16* sV = sK + ROWS * PITCH;
-  float* sT = reinterpret_cast<float*>(sV + ROWS * PITCH);
+  bf16* sK = sQ + QROWS * PITCH;
+  bf16* sV = sK + KROWS * PITCH;
+  float* sT = reinterpret_cast<float*>(sV + KROWS * PITCH) + TPAD;
 
-  // ---- stage q, k, v (16-byte chunks, 4 per 32-channel head slice) and the bias table (pre-multiplied by log2 e)
-  for (int i = ltid; i < 3 * ROWS * 4; i += GT) {
-    const int part = i / (ROWS * 4);
-    const int rem = i - part * (ROWS * 4);
-    const int r = rem >> 2, ch = rem & 3;
-    const bool valid = r < N;
-    const int rr = valid ? r : 0;
-    const int y = wy * WS + rr / WS, x = wx * WS + rr % WS;
-    const long long row = ((long long)b * H + y) * W + x;
+  // ---- stage q (token order), k / v (padded key order: row = window row * WP + window column; padding rows are zero)
+  //      and the bias table (pre-multiplied by log2 e); 16-byte chunks, 4 per 32-channel head slice
+  for (int i = ltid; i < (QROWS + 2 * KROWS) * 4; i += GT) {
+    const int r = i >> 2, ch = i & 3;
+    bool valid;
+    int tok;
     const bf16* src;
-    if (part == 0) src = global_q ? qg + ((long long)b * N + rr) * C + h * HD : qkv + row * ldq + h * HD;
-    else src = qkv + row * ldq + (part == 1 ? koff : voff);
-    cp_async16_zfill(sQ + (part * ROWS + r) * PITCH + ch * 8, src + ch * 8, valid);
+    if (r < QROWS) {
+      valid = r < N;
+      tok = valid ? r : 0;
+    } else {
+      const int pr = (r - QROWS) % KROWS;
+      const int ky = pr / WP, kx = pr % WP;
+      valid = ky < WS && kx < WS;
+      tok = valid ? ky * WS + kx : 0;
+    }
+    const int y = wy * WS + tok / WS, x = wx * WS + tok % WS;
+    const long long row = ((long long)b * H + y) * W + x;
+    if (r < QROWS) src = global_q ? qg + ((long long)b * N + tok) * C + h * HD : qkv + row * ldq + h * HD;
+    else src = qkv + row * ldq + (r < QROWS + KROWS ? koff : voff);
+    cp_async16_zfill(sQ + r * PITCH + ch * 8, src + ch * 8, valid);
   }
   for (int i = ltid; i < TAB; i += GT) sT[i] = __ldg(table + (long long)h * TAB + i) * 1.4426950408889634f;
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -117,8 +135,7 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const bf16* _
   else __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
-  for (int mt = w_in_pair; mt < KT; mt += WPP) {
-    // ---- S = Q K^T for 16 query rows
+  for (int mt = w_in_pair; mt < QT; mt += WPP) {
     uint32_t qa[2][4];
     {
       const uint32_t* q0 = reinterpret_cast<const uint32_t*>(sQ + (mt * 16 + g) * PITCH);
@@ -131,75 +148,101 @@ __global__ void __launch_bounds__(128) window_attention_mma_kernel(const bf16* _
         qa[ks][3] = q1[ks * 8 + 4 + t];
       }
     }
-    float s[NT][4];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * PITCH);
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) mma16816(s[nt], qa[ks], kr[ks * 8 + t], kr[ks * 8 + 4 + t]);
-    }
-    // ---- softmax over the keys (rows r0 = mt*16+g and r1 = r0+8; each row lives in the 4 lanes of a quad)
+    // bias rows of the two query rows this lane holds (r0 = mt*16+g, r1 = r0+8): sT[qo - ky*(2WS-1) - kx]
     const int r0 = min(mt * 16 + g, N - 1), r1 = min(mt * 16 + g + 8, N - 1);
-    const int qo0 = (r0 / WS + WS - 1) * (2 * WS - 1) + r0 % WS + WS - 1;
-    const int qo1 = (r1 / WS + WS - 1) * (2 * WS - 1) + r1 % WS + WS - 1;
-    float m0 = -3.0e38f, m1 = -3.0e38f;
+    const float* pb0 = sT + (r0 / WS + WS - 1) * (2 * WS - 1) + r0 % WS + WS - 1 - 2 * t;
+    const float* pb1 = sT + (r1 / WS + WS - 1) * (2 * WS - 1) + r1 % WS + WS - 1 - 2 * t;
+    float m0 = -3.0e38f, m1 = -3.0e38f, l0 = 0.0f, l1 = 0.0f;
+    float o[4][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + 2 * t + e;
-        if (j < N) {
-          const int ko = j + (WS - 1) * (j / WS);
-          s[nt][e] = fmaf(s[nt][e], scale_log2e, sT[qo0 - ko]);
-          s[nt][2 + e] = fmaf(s[nt][2 + e], scale_log2e, sT[qo1 - ko]);
-        } else {
-          s[nt][e] = -3.0e38f;
-          s[nt][2 + e] = -3.0e38f;
+    for (int blk = 0; blk < NB; ++blk) {
+      // ---- S = Q K^T for 16 query rows x NTB key tiles
+      float s[NTB][4];
+#pragma unroll
+      for (int i = 0; i < NTB; ++i) {
+        const int nt = blk * NTB + i;
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
+        if ((nt * 8) / WP < WS) {  // a tile of padding keys only needs no product
+          const uint32_t* kr = reinterpret_cast<const uint32_t*>(sK + (nt * 8 + g) * PITCH);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) mma16816(s[i], qa[ks], kr[ks * 8 + t], kr[ks * 8 + 4 + t]);
         }
-        m0 = fmaxf(m0, s[nt][e]);
-        m1 = fmaxf(m1, s[nt][2 + e]);
       }
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.0f, l1 = 0.0f;
+      // ---- scale + relative position bias, mask the padding keys, block maximum
+      float mb0 = -3.0e38f, mb1 = -3.0e38f;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = fast_exp2(s[nt][0] - m0);
-      s[nt][1] = fast_exp2(s[nt][1] - m0);
-      s[nt][2] = fast_exp2(s[nt][2] - m1);
-      s[nt][3] = fast_exp2(s[nt][3] - m1);
-      l0 += s[nt][0] + s[nt][1];
-      l1 += s[nt][2] + s[nt][3];
+      for (int i = 0; i < NTB; ++i) {
+        const int nt = blk * NTB + i;
+        const int ky = (nt * 8) / WP, kx0 = (nt * 8) % WP;  // compile-time
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          // kx = kx0 + 2t + e is a real window column iff < WS
+          const bool real = ky < WS && (kx0 + 7 < WS || kx0 + 2 * t + e < WS);
+          if (real) {
+            const int off = -(ky * (2 * WS - 1) + kx0 + e);
+            s[i][e] = fmaf(s[i][e], scale_log2e, pb0[off]);
+            s[i][2 + e] = fmaf(s[i][2 + e], scale_log2e, pb1[off]);
+          } else {
+            s[i][e] = -3.0e38f;
+            s[i][2 + e] = -3.0e38f;
+          }
+          mb0 = fmaxf(mb0, s[i][e]);
+          mb1 = fmaxf(mb1, s[i][2 + e]);
+        }
+      }
+      mb0 = fmaxf(mb0, __shfl_xor_sync(0xffffffffu, mb0, 1));
+      mb0 = fmaxf(mb0, __shfl_xor_sync(0xffffffffu, mb0, 2));
+      mb1 = fmaxf(mb1, __shfl_xor_sync(0xffffffffu, mb1, 1));
+      mb1 = fmaxf(mb1, __shfl_xor_sync(0xffffffffu, mb1, 2));
+      const float mn0 = fmaxf(m0, mb0), mn1 = fmaxf(m1, mb1);
+      if (NB > 1) {  // online softmax: rescale what the earlier key blocks contributed
+        const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
+        l0 *= c0;
+        l1 *= c1;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          o[nt][0] *= c0;
+          o[nt][1] *= c0;
+          o[nt][2] *= c1;
+          o[nt][3] *= c1;
+        }
+      }
+      m0 = mn0;
+      m1 = mn1;
+#pragma unroll
+      for (int i = 0; i < NTB; ++i) {
+        s[i][0] = fast_exp2(s[i][0] - m0);
+        s[i][1] = fast_exp2(s[i][1] - m0);
+        s[i][2] = fast_exp2(s[i][2] - m1);
+        s[i][3] = fast_exp2(s[i][3] - m1);
+        l0 += s[i][0] + s[i][1];
+        l1 += s[i][2] + s[i][3];
+      }
+      // ---- O += P V
+#pragma unroll
+      for (int kk = 0; kk < KTB; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int mj = lane >> 3;  // which 8x8 matrix this lane addresses
+        const bf16* vrow = sV + ((blk * KTB + kk) * 16 + (mj & 1) * 8 + (lane & 7)) * PITCH + (mj >> 1) * 8;
+#pragma unroll
+        for (int dp = 0; dp < 2; ++dp) {
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, vrow + dp * 16);
+          mma16816(o[2 * dp], pa, vb[0], vb[1]);
+          mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
+        }
+      }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    // ---- O = P V
-    float o[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
-#pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      const int mj = lane >> 3;  // which 8x8 matrix this lane addresses
-      const bf16* vrow = sV + (kk * 16 + (mj & 1) * 8 + (lane & 7)) * PITCH + (mj >> 1) * 8;
-#pragma unroll
-      for (int dp = 0; dp < 2; ++dp) {
-        uint32_t vb[4];
-        ldmatrix_x4_trans(vb, vrow + dp * 16);
-        mma16816(o[2 * dp], pa, vb[0], vb[1]);
-        mma16816(o[2 * dp + 1], pa, vb[2], vb[3]);
-      }
-    }
     // ---- normalise, stage through the consumed q rows, coalesced store
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     __syncwarp();
@@ -251,6 +294,11 @@ int launch_attention(const bf16* qkv, const bf16* qg, const float* table, bf16* 
 }  // namespace
 }  // namespace vip
 
+namespace vip {
+int window_attention_tc(const void* qkv, const void* qg, const float* table, void* out, int B, int H, int W, int C, int ws,
+                        int heads, cudaStream_t st);
+}
+
 extern "C" int vip_window_attention_bf16(const void* qkv, const void* q_global, const float* rel_table, void* out, int B,
                                          int H, int W, int C, int ws, int heads, void* stream) {
   using namespace vip;
@@ -260,6 +308,13 @@ extern "C" int vip_window_attention_bf16(const void* qkv, const void* q_global, 
               heads);
   VIP_REQUIRE(H % ws == 0 && W % ws == 0, VIP_ERR_INVALID, "vip_window_attention_bf16: H, W must be multiples of ws");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // Two implementations, same results.  Measured on B200 (batch 256, profiles/README.md): the warp-level mma.sync kernel
+  // of this file runs at the legacy-HMMA roofline of sm_100 (ws 14: 87 us, ws 7 @56x56: 199 us); the tcgen05 kernel
+  // (attention_tc.cu: S and O in TMEM, P fed to the second product straight from TMEM) removes the MMA bound but its
+  // unspecialised load -> MMA -> softmax -> MMA -> store sequence is latency-bound (100 / 258 us).  Until that kernel is
+  // warp-specialised the mma.sync one is the default; VIP_ATTN_TCGEN05=1 selects the other.
+  static const bool use_tc = [] { const char* v = getenv("VIP_ATTN_TCGEN05"); return v != nullptr && v[0] == '1'; }();
+  if (use_tc && (ws == 7 || ws == 14)) return window_attention_tc(qkv, q_global, rel_table, out, B, H, W, C, ws, heads, st);
   if (ws == 7)
     return launch_attention<7>((const bf16*)qkv, (const bf16*)q_global, rel_table, (bf16*)out, B, H, W, C, heads, st);
   if (ws == 14)

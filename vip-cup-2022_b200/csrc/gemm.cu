@@ -17,6 +17,7 @@
 //               beyond M and columns beyond N are clipped by the TMA unit).  Optional row statistics (for the
 //               LayerNorm folded into the NEXT contraction) and global-average-pool partial sums are accumulated here.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm.cuh"
 
@@ -44,8 +45,10 @@ __global__ void init_neutral_kernel() {
 struct GemmArgs {
   int M, N, K;
   int num_kb, m_tiles, n_tiles;
-  int conv;  // 1: A operand comes from the im2col map
+  int conv;  // 0: plain GEMM; 1: A from the im2col-mode map (linear pixel tiles); 2: A from a tiled 4-D map (patch tiles)
   int cblocks, C, ks, stride, pad, Wo, HoWo;
+  // patch tiles (conv == 2): a tile is bni images x bh rows x bw columns of the output (<= 128 pixels)
+  int bw, bh, bni, tiles_w, tiles_h, prow, Ho, Nimg;
   int mode;  // EpiMode
   GemmEpilogue epi;
 };
@@ -90,6 +93,19 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtenso
       "[%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
       "l"(tmap), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
@@ -323,23 +339,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
         int cw = 0, ch = 0, cn = 0;
-        if (g.conv) {
+        if (g.conv == 1) {
           cn = m0 / g.HoWo;
           const int rem = m0 - cn * g.HoWo;
           const int p0 = rem / g.Wo, q0 = rem - p0 * g.Wo;
           cw = q0 * g.stride - g.pad;
           ch = p0 * g.stride - g.pad;
+        } else if (g.conv == 2) {
+          const int mt = tile / g.n_tiles;
+          const int pw = mt % g.tiles_w, t2 = mt / g.tiles_w;
+          cw = pw * g.bw * g.stride - g.pad;
+          ch = (t2 % g.tiles_h) * g.bh * g.stride - g.pad;
+          cn = (t2 / g.tiles_h) * g.bni;
         }
+        const uint32_t stage_tx = (g.conv == 2 ? (uint32_t)g.prow * 128u : (uint32_t)kABytes) + (uint32_t)C::kBBytes;
         for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], C::kStageBytes);
+          mbar_expect_tx(&full_bar[s], stage_tx);
           uint8_t* a_dst = smem + s * C::kStageBytes;
           if (g.conv) {
             const int tap = kb / g.cblocks, cb = kb - tap * g.cblocks;
             const int r = tap / g.ks, sx = tap - r * g.ks;
-            tma_load_im2col_4d(a_dst, &tmA, &full_bar[s], cb * BK, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+            if (g.conv == 1) tma_load_im2col_4d(a_dst, &tmA, &full_bar[s], cb * BK, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+            else tma_load_4d(a_dst, &tmA, &full_bar[s], cb * BK, cw + sx, ch + r, cn);
             tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], tap * g.C + cb * BK, n0);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
@@ -409,6 +433,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       const int row = m0 + rt;
+      int pq0 = 0, pp0 = 0, pn0 = 0;  // patch tile origin (output column, row, image)
+      if (g.conv == 2) {
+        const int mt = tile / g.n_tiles;
+        const int t2 = mt / g.tiles_w;
+        pq0 = (mt % g.tiles_w) * g.bw;
+        pp0 = (t2 % g.tiles_h) * g.bh;
+        pn0 = (t2 / g.tiles_h) * g.bni;
+      }
       float rstd = 1.0f, nmr = 0.0f;  // 1/sigma and -mean/sigma of this row (identity without a folded LayerNorm)
       if (e.ln_stats != nullptr) {
         const float2 st = st_next;
@@ -501,9 +533,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         epi_bar_sync();
         if (te == 0 && e.out_bf16 != nullptr) {
-          tma_store_2d(&tmC, cbase, n0 + j * 64, m0);
+          if (g.conv == 2) tma_store_4d(&tmC, cbase, n0 + j * 64, pq0, pp0, pn0);
+          else tma_store_2d(&tmC, cbase, n0 + j * 64, m0);
           tma_store_commit();
         }
+        if (e.gap != nullptr && g.conv == 2) {
+          // patch tile: row r = ((image, patch row, patch column)); rows outside the map / batch are skipped
+          const int cpair = te & 31, rq = te >> 5;
+          const int n = n0 + j * 64 + cpair * 2;
+          if (n < g.N) {
+            const int per_img = g.bw * g.bh;
+            float s0 = 0.0f, s1 = 0.0f;
+            int cur = -1;
+            for (int k = 0; k < 16; ++k) {
+              const int rr = rq * 16 + k;
+              if (rr >= g.prow) break;
+              const int ni = rr / per_img, rem = rr - ni * per_img;
+              const int py = rem / g.bw, px = rem - py * g.bw;
+              if (pn0 + ni >= g.Nimg || pp0 + py >= g.Ho || pq0 + px >= g.Wo) continue;
+              if (ni != cur) {
+                if (cur >= 0) {
+                  atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+                  atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+                }
+                s0 = s1 = 0.0f;
+                cur = ni;
+              }
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(
+                  cbase + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) + (cpair & 3) * 4);
+              s0 += __uint_as_float(w << 16);
+              s1 += __uint_as_float(w & 0xffff0000u);
+            }
+            if (cur >= 0) {
+              atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+              atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+            }
+          }
+        } else
         if (e.gap != nullptr) {
           // column sums of the staged bf16 chunk, split at image boundaries: thread -> (2 columns, 16 rows)
           const int cpair = te & 31, rq = te >> 5;
@@ -598,6 +664,23 @@ int make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& c) {
   return VIP_OK;
 }
 
+// NHWC tensor as a 4-D tiled map (C, W, H, N): box = 64 channels x bw x bh x bni positions taken every `stride`
+int make_tmap_nhwc(CUtensorMap* tm, const void* base, int Nimg, int H, int W, int C, int bw, int bh, int bni, int stride) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
+  VIP_REQUIRE(fn != nullptr, VIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+  const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bni};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VIP_REQUIRE(r == CUDA_SUCCESS, VIP_ERR_CUDA,
+              "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d (N=%d H=%d W=%d C=%d box %dx%dx%d stride %d)", (int)r,
+              Nimg, H, W, C, bw, bh, bni, stride);
+  return VIP_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -637,24 +720,27 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   return VIP_OK;
 }
 
-// tile width: trade column padding, wave quantisation over the resident CTAs and per-tile efficiency
-int pick_bn(long long M, int N, bool deep, bool conv) {
+// Tile width by a small cost model (cycles per tile x waves over the resident CTAs).  Per k-block a tile needs
+// max(MMA issue: 2*bn cycles for M=128, operand delivery: bytes / ~64 B/clk/SM from L2 -- an im2col-mode A k-block takes
+// ~650 cycles whatever the width); its epilogue needs ~600 cycles per 64-column chunk (halved when two CTAs share the SM).
+int pick_bn(long long M, int N, bool deep, bool conv, int num_kb) {
   const int slots = num_sms() * (deep ? 1 : 2);
   const long long mt = (M + BM - 1) / BM;
   int best = 64;
-  double best_score = -1.0;
+  double best_cost = 1e30;
   for (int bn : {256, 128, 64}) {
     if (!deep && bn == 256) continue;
     const int nt = (N + bn - 1) / bn;
     const long long tiles = mt * nt;
-    const double col_eff = (double)N / ((double)nt * bn);
+    const double load = conv ? 650.0 + bn * 128 / 64.0 : (kABytes + bn * 128) / 64.0;
+    const double mma = 2.0 * bn;
+    const double main = num_kb * (load > mma ? load : mma);
+    const int chunks = (N < bn ? N + 63 : bn) / 64;
+    const double epi = chunks * (deep ? 600.0 : 300.0);
+    const double per_tile = (main > epi ? main : epi) + 200.0;
     const double waves = (double)((tiles + slots - 1) / slots);
-    const double wave_eff = (double)tiles / (waves * slots);
-    // im2col-mode TMA delivers an A k-block in ~650 cycles whatever the tile width, so a convolution tile costs the
-    // same time at every BN: prefer the widest one
-    const double tile_eff = conv ? (bn == 256 ? 1.0 : bn == 128 ? 0.55 : 0.3) : (bn == 256 ? 1.0 : bn == 128 ? 0.97 : 0.88);
-    const double score = col_eff * wave_eff * tile_eff;
-    if (score > best_score) { best_score = score; best = bn; }
+    const double cost = waves * per_tile * (deep ? 1.0 : 2.0);  // two co-resident CTAs share the SM's bandwidth
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -691,18 +777,20 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
 }
 
 int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, int N, int K, GemmArgs& g,
-        const GemmEpilogue& epi, cudaStream_t stream) {
+        const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* tmC_patch = nullptr) {
   VIP_REQUIRE(N <= kMaxCols, VIP_ERR_UNSUPPORTED, "gemm: N = %d exceeds %d", N, kMaxCols);
   int rc0 = ensure_neutral(stream);
   if (rc0 != VIP_OK) return rc0;
   const bool deep = g.num_kb > 4;  // K > 256: the MMA loop dominates; otherwise the epilogue does
-  const int bn = pick_bn(M, N, deep, g.conv != 0);
+  const int bn = pick_bn(M, N, deep, g.conv == 1, g.num_kb);
   CUtensorMap tmB, tmC, tmR;
   int rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
   if (rc != VIP_OK) return rc;
   tmC = tmB;
   tmR = tmB;
-  if (epi.out_bf16 != nullptr) {
+  if (tmC_patch != nullptr) {
+    tmC = *tmC_patch;
+  } else if (epi.out_bf16 != nullptr) {
     rc = make_tmap_2d(&tmC, epi.out_bf16, M, N, epi.ldc, BM);
     if (rc != VIP_OK) return rc;
   }
@@ -759,22 +847,81 @@ int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* 
   VIP_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, VIP_ERR_INVALID, "conv2d_bf16: unaligned operand");
   int rc = check_epilogue(epi, Cout);
   if (rc != VIP_OK) return rc;
-  CUtensorMap tmA;
-  rc = make_tmap_im2col(&tmA, x, c);
-  if (rc != VIP_OK) return rc;
   GemmArgs g{};
-  g.conv = 1;
   g.cblocks = (c.C + BK - 1) / BK;
   g.C = c.C;
   g.ks = c.ksize;
   g.stride = c.stride;
   g.pad = c.pad;
   g.Wo = c.Wo;
+  g.Ho = c.Ho;
+  g.Nimg = c.Nimg;
   g.HoWo = c.Ho * c.Wo;
   g.num_kb = c.ksize * c.ksize * g.cblocks;
   const long long M = (long long)c.Nimg * c.Ho * c.Wo;
   VIP_REQUIRE(M < (1LL << 31), VIP_ERR_UNSUPPORTED, "conv2d_bf16: too many output pixels");
-  return run(tmA, w, ldw, M, Cout, c.ksize * c.ksize * c.C, g, epi, stream);
+  const int K = c.ksize * c.ksize * c.C;
+  const bool deep = g.num_kb > 4;
+
+  // Two ways to feed the A operand.  im2col-mode TMA packs 128 consecutive output pixels per tile (no padding rows) but
+  // delivers a k-block in ~650 cycles; a tiled 4-D box (a patch of bni x bh x bw output pixels, shifted per filter tap,
+  // zero-filled outside the image) arrives ~4x faster but wastes the rows the patch shape cannot fill.  Pick by a
+  // simple cost model: tiles x max(load cycles, MMA cycles) per k-block.
+  int bw = 0, bh = 0, bni = 0;
+  long long patches = 0;
+  {
+    double best = 0.0;
+    for (int w_ = c.Wo < 128 ? c.Wo : 128; w_ >= 1; --w_) {
+      if (w_ * c.stride > 256) continue;
+      int h_ = 128 / w_;
+      if (h_ > c.Ho) h_ = c.Ho;
+      if (h_ * c.stride > 256) h_ = 256 / c.stride;
+      int n_ = (h_ == c.Ho && w_ == c.Wo) ? 128 / (w_ * h_) : 1;
+      if (n_ > c.Nimg) n_ = c.Nimg;
+      if (n_ < 1) n_ = 1;
+      const long long t = (long long)((c.Wo + w_ - 1) / w_) * ((c.Ho + h_ - 1) / h_) * ((c.Nimg + n_ - 1) / n_);
+      const double eff = (double)M / ((double)t * BM);
+      if (eff > best + 1e-9) { best = eff; bw = w_; bh = h_; bni = n_; patches = t; }
+    }
+  }
+  const bool patch_ok = epi.out_bf16 != nullptr && epi.residual == nullptr && epi.row_stats == nullptr &&
+                        epi.ln_stats == nullptr && epi.row_gate == nullptr && patches > 0 && patches * BM < (1LL << 31);
+  // Measured on B200: both feeds run at the same ~650 cycles per k-block (the 9x re-read of the input through L2 is the
+  // limit, not the TMA mode), so the patch tiles' padding rows are pure loss; the path stays selectable for experiments
+  // (VIP_CONV_PATCH=1) and as the base of a halo-reuse variant.
+  static const bool patch_env = [] { const char* v = getenv("VIP_CONV_PATCH"); return v != nullptr && v[0] == '1'; }();
+  const bool use_patch = patch_ok && patch_env;
+  CUtensorMap tmA;
+  if (!use_patch) {
+    rc = make_tmap_im2col(&tmA, x, c);
+    if (rc != VIP_OK) return rc;
+    g.conv = 1;
+    return run(tmA, w, ldw, M, Cout, K, g, epi, stream);
+  }
+  rc = make_tmap_nhwc(&tmA, x, c.Nimg, c.H, c.W, c.C, bw, bh, bni, c.stride);
+  if (rc != VIP_OK) return rc;
+  CUtensorMap tmC;
+  {
+    // output [Nimg, Ho, Wo, ldc]: same patch box, unit stride; only the first Cout channels of a row are addressed
+    static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
+    VIP_REQUIRE(fn != nullptr, VIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t gdim[4] = {(cuuint64_t)Cout, (cuuint64_t)c.Wo, (cuuint64_t)c.Ho, (cuuint64_t)c.Nimg};
+    const cuuint64_t gstride[3] = {(cuuint64_t)epi.ldc * 2, (cuuint64_t)c.Wo * epi.ldc * 2, (cuuint64_t)c.Ho * c.Wo * epi.ldc * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bni};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, epi.out_bf16, gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VIP_REQUIRE(r == CUDA_SUCCESS, VIP_ERR_CUDA, "cuTensorMapEncodeTiled (conv output) failed with CUresult %d", (int)r);
+  }
+  g.conv = 2;
+  g.bw = bw;
+  g.bh = bh;
+  g.bni = bni;
+  g.tiles_w = (c.Wo + bw - 1) / bw;
+  g.tiles_h = (c.Ho + bh - 1) / bh;
+  g.prow = bw * bh * bni;
+  return run(tmA, w, ldw, patches * BM, Cout, K, g, epi, stream, &tmC);
 }
 
 }  // namespace vip
