@@ -7,6 +7,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("m,n,k", [
     (128, 32, 64), (128, 128, 64), (256, 256, 256), (1000, 64, 288), (625 * 3, 512, 1152), (49 * 5, 2048, 512),
     (130, 192 + 64, 96), (4096, 768, 256), (77, 32, 8), (20000, 64, 576),
+    # K > 256 and N >= 128: two-CTA (cta_group::2) tiles of 256 rows, incl. ragged M / N / K tails
+    (5000, 384, 768), (300, 256, 512), (33000, 1152, 384), (257, 128, 320), (1024, 1000, 520),
 ])
 @pytest.mark.parametrize("epi", ["plain", "bias_relu_res", "gelu_f32", "colscale_res"])
 def test_gemm_matches_torch(cuda_device, m, n, k, epi):

@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libvipcup.so cannot be built")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), *sources(), "-o", LIB + ".tmp"]
+    extra = os.environ.get("VIP_NVCC_EXTRA", "").split()   # e.g. -DVIP_MBAR_DEBUG (barrier watchdog for kernel bring-up)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), *sources(), "-o", LIB + ".tmp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -17,6 +17,7 @@
 //               beyond M and columns beyond N are clipped by the TMA unit).  Optional row statistics (for the
 //               LayerNorm folded into the NEXT contraction) and global-average-pool partial sums are accumulated here.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "gemm.cuh"
@@ -50,6 +51,8 @@ struct GemmArgs {
   // patch tiles (conv == 2): a tile is bni images x bh rows x bw columns of the output (<= 128 pixels)
   int bw, bh, bni, tiles_w, tiles_h, prow, Ho, Nimg;
   int mode;  // EpiMode
+  int dbg;            // experiments: 4 = MMA warp does not wait for operands, 8 = MMA warp issues no MMAs
+  long long* trace;  // VIP_GEMM_TRACE=1: per-tile clock64() stamps of CTA 0 ([tile][8]); null otherwise
   GemmEpilogue epi;
 };
 
@@ -64,6 +67,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef VIP_MBAR_DEBUG
+// debug build: a wait that does not complete within ~2^27 polls reports where it is stuck and traps
+__device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+  for (unsigned long long n = 0;; ++n) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (n > (1ull << 25)) {
+      printf("mbar stuck: line %d block %d thread %d parity %u\n", line, (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -73,6 +95,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
+// polling wait (mbarrier.test_wait): for barriers whose arrivals come from the OTHER CTA of a pair; a thread parked in
+// try_wait is not woken promptly by remote arrivals
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SPIN_%=:\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SDONE_%=;\n"
+      "bra SPIN_%=;\n"
+      "SDONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
@@ -117,6 +155,49 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair-mode TMA load: data lands in this CTA's shared memory, the bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -175,17 +256,22 @@ __device__ __forceinline__ float gelu_fast(float x) {
 
 // kDeep: one CTA per SM with a deep operand ring (long K loops).  !kDeep: two CTAs per SM with a short ring, for the
 // output-heavy contractions (K <= 256) whose time goes into the epilogue; BN <= 128 so that both CTAs get TMEM.
-template <int BN, bool kDeep>
+// kPair (implies kDeep): a cluster of two CTAs on the two SMs of a TPC computes one 256 x BN tile with
+// tcgen05.mma.cta_group::2: each CTA stages its own 128 rows of A and HALF of the B k-block, the leader's MMA reads both
+// halves.  Operand traffic into each SM's shared memory drops by a third (BN = 256), which is what bounds the
+// single-CTA kernel (A + B fill plus the MMA's own reads exceed the 128 B/clk of shared memory).
+template <int BN, bool kDeep, bool kPair = false>
 struct Cfg {
-  static constexpr int kStages = kDeep ? (BN == 256 ? 3 : BN == 128 ? 5 : 6) : (BN == 128 ? 2 : 3);
+  static constexpr int kBBytes = (kPair ? BN / 2 : BN) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kPair ? (BN == 256 ? 5 : 6) : kDeep ? (BN == 256 ? 3 : BN == 128 ? 5 : 6) : (BN == 128 ? 2 : 3);
   static constexpr int kCBufs = kDeep ? 4 : 2;   // ring of output staging buffers (one 64-column chunk each)
   static constexpr int kMinBlocks = kDeep ? 1 : 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kChunks = BN / 64;   // 64-column chunks per tile
   static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: a power of two
   static constexpr int kSmem = kStages * kStageBytes + kCBufs * kCBufBytes + 1024 + 256;
   static_assert(kDeep || BN <= 128, "two CTAs per SM need at most 256 TMEM columns each");
+  static_assert(!kPair || (kDeep && BN >= 128), "pair mode is a deep-ring configuration");
 };
 
 // One group of 8 output columns of one row: folded LayerNorm + bias (2 FMAs), activation, column scale.
@@ -207,6 +293,8 @@ __device__ __forceinline__ void epi_group(float (&v)[8], float rstd, float nmr, 
     v[i] = t * sc[i];
   }
 }
+
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // Specialised epilogues (compile-time feature sets) for the combinations the backbones use; everything else takes the
 // generic path with neutral parameter vectors.
@@ -279,11 +367,62 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
   }
 }
 
-template <int BN, bool kDeep>
-__global__ void __launch_bounds__(kThreads, Cfg<BN, kDeep>::kMinBlocks)
+// Every other feature combination: neutral parameter vectors, run-time activation, bf16 or f32 output.
+__device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
+                                              int N, int row, int M, const GemmEpilogue& e, bool has_res, float rstd,
+                                              float nmr, const float* __restrict__ p_colsum,
+                                              const float* __restrict__ p_bias, const float* __restrict__ p_colscale,
+                                              float& rs_sum, float& rs_sq) {
+#pragma unroll
+  for (int q8 = 0; q8 < 4; ++q8) {
+    const int n = nb + q8 * 8;
+    if (n >= N) break;  // N % 8 == 0: a group of 8 columns is entirely inside or outside
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q8 * 8 + i]);
+    switch (e.act) {
+      case ACT_RELU: epi_group<ACT_RELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+      case ACT_GELU: epi_group<ACT_GELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+      case ACT_SIGMOID: epi_group<ACT_SIGMOID>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+      default: epi_group<ACT_NONE>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+    }
+    uint4* cp = reinterpret_cast<uint4*>(crow + ((cbase16 + q8) ^ swz) * 16);
+    if (has_res) {
+      const uint4 u = *cp;
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        v[2 * t] += __uint_as_float(w[t] << 16);
+        v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
+      }
+    }
+    if (e.out_bf16 != nullptr) {
+      uint32_t w[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+        w[t] = *reinterpret_cast<const uint32_t*>(&h2);
+        const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+        rs_sum += lo + hi;
+        rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
+      }
+      *cp = make_uint4(w[0], w[1], w[2], w[3]);
+    } else if (row < M) {
+      float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
+      op[0] = make_float4(v[0], v[1], v[2], v[3]);
+      op[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+template <int BN, bool kDeep, bool kPair = false>
+__global__ void __launch_bounds__(kThreads, Cfg<BN, kDeep, kPair>::kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
-  using C = Cfg<BN, kDeep>;
+  using C = Cfg<BN, kDeep, kPair>;
+  constexpr int kCtas = kPair ? 2 : 1;          // CTAs that share one tile
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int cta_tile0 = blockIdx.x / kCtas, cta_tile_step = gridDim.x / kCtas;
   constexpr int kStages = C::kStages;
   constexpr int kCBufs = C::kCBufs;
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +434,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator stage drained by the epilogue
   uint64_t* rfull_bar = tempty_bar + 2;        // [kCBufs] residual chunk landed in a staging buffer
   uint64_t* cfree_bar = rfull_bar + kCBufs;    // [kCBufs] staging buffer free for the next residual chunk
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfree_bar + kCBufs);
+  uint64_t* pfull_bar = cfree_bar + kCBufs;    // [kStages] pair mode, leader only: the PEER's ring slot has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pfull_bar + kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = g.m_tiles * g.n_tiles;
@@ -310,10 +450,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&pfull_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[s], 8 * kCtas);  // one arrival per epilogue warp (of both CTAs in pair mode)
     }
     for (int b = 0; b < kCBufs; ++b) {
       mbar_init(&rfull_bar[b], 1);
@@ -322,22 +463,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // both CTAs' barriers are initialised before anything arrives on them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      uint32_t it = 0, cc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
+      uint32_t it = 0, tcountp = 0;
+      for (int tile = cta_tile0; tile < total_tiles; tile += cta_tile_step) {
+        const int m0 = ((tile / g.n_tiles) * kCtas + (int)cta_rank) * BM, n0 = (tile % g.n_tiles) * BN;
         int cw = 0, ch = 0, cn = 0;
         if (g.conv == 1) {
           cn = m0 / g.HoWo;
@@ -353,12 +502,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           cn = (t2 / g.tiles_h) * g.bni;
         }
         const uint32_t stage_tx = (g.conv == 2 ? (uint32_t)g.prow * 128u : (uint32_t)kABytes) + (uint32_t)C::kBBytes;
+        if (g.trace != nullptr && blockIdx.x == 0) g.trace[(tile / cta_tile_step) * 16 + 0] = clock64();
         for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], stage_tx);
+          if (kPair) mbar_wait_spin(&empty_bar[s], ph ^ 1);
+          else mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = smem + s * C::kStageBytes;
+          if (kPair) {
+            // this CTA stages its 128 rows of A and its half of the B k-block; completion stays on the LOCAL barrier
+            // (crediting the peer's bytes to the leader's barrier directly costs one cross-SM message per 128-byte row
+            // and throttles the ring to ~20 B/clk; the peer forwards ONE arrival per slot instead, see the MMA warp)
+            mbar_expect_tx(&full_bar[s], stage_tx);
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
+            tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0 + (int)cta_rank * (BN / 2));
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], stage_tx);
           if (g.conv) {
             const int tap = kb / g.cblocks, cb = kb - tap * g.cblocks;
             const int r = tap / g.ks, sx = tap - r * g.ks;
@@ -370,16 +530,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0);
           }
         }
+        if (g.trace != nullptr && blockIdx.x == 0) g.trace[(tile / cta_tile_step) * 16 + 1] = clock64();
         if (has_res) {
-          // after this tile's operand loads are in flight: bring the residual chunks into the staging ring, each as
-          // soon as the store that last used its buffer has finished reading it
-          for (int j = 0; j < C::kChunks && n0 + j * 64 < g.N; ++j, ++cc) {
-            const uint32_t b = cc % kCBufs, u = cc / kCBufs;
+          // after this tile's operand loads are in flight: bring the residual chunks into the staging buffers of this
+          // tile's set, each as soon as the store that last used the buffer has finished reading it.  Every buffer of
+          // the set takes part in the handshake, also the ones a ragged last N tile does not fill.
+          constexpr int kSetsP = kCBufs / C::kChunks;
+          const uint32_t set = tcountp % kSetsP, u = tcountp / kSetsP;
+          for (int j = 0; j < C::kChunks; ++j) {
+            const uint32_t b = set * C::kChunks + j;
             mbar_wait(&cfree_bar[b], (u & 1) ^ 1);
-            mbar_expect_tx(&rfull_bar[b], kCBufBytes);
-            tma_load_2d(cbuf + b * kCBufBytes, &tmR, &rfull_bar[b], n0 + j * 64, m0);
+            if (n0 + j * 64 < g.N) {
+              mbar_expect_tx(&rfull_bar[b], kCBufBytes);
+              tma_load_2d(cbuf + b * kCBufBytes, &tmR, &rfull_bar[b], n0 + j * 64, m0);
+            } else {
+              mbar_arrive(&rfull_bar[b]);
+            }
           }
         }
+        ++tcountp;
       }
     }
   } else if (warp == 1) {
@@ -387,52 +556,91 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       // instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t idesc_pair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      if (kPair && cta_rank != 0) {
+        // peer CTA: no MMAs to issue; tell the leader when each of this CTA's ring slots has landed
+        for (int tile = cta_tile0; tile < total_tiles; tile += cta_tile_step) {
+          for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&full_bar[s], (it / kStages) & 1);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&pfull_bar[s]), 0));
+          }
+        }
+      }
+      it = 0;
+      for (int tile = cta_tile0; tile < total_tiles && cta_rank == 0; tile += cta_tile_step, ++tcount) {
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aph ^ 1);
+        if (kPair) mbar_wait_spin(&tempty_bar[as], aph ^ 1);
+        else mbar_wait(&tempty_bar[as], aph ^ 1);
         tcgen05_fence_after();
+        if (g.trace != nullptr && blockIdx.x == 0) g.trace[(tile / cta_tile_step) * 16 + 2] = clock64();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (!(g.dbg & 4)) {
+            mbar_wait(&full_bar[s], ph);
+            if (kPair) mbar_wait_spin(&pfull_bar[s], ph);
+          }
           tcgen05_fence_after();
+          if (g.trace != nullptr && blockIdx.x == 0 && kb == 0) g.trace[(tile / cta_tile_step) * 16 + 3] = clock64();
           const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
           const uint64_t a_desc = make_sw128_desc(a_addr);
           const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (g.dbg & 8) break;
             // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kPair) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // implies tcgen05.fence::before_thread_sync
+          // implies tcgen05.fence::before_thread_sync; pair mode: releases the ring slot in BOTH CTAs
+          if (kPair) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[as]);
+        if (kPair) umma_commit_pair(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
+        if (g.trace != nullptr && blockIdx.x == 0) g.trace[(tile / cta_tile_step) * 16 + 4] = clock64();
       }
     }
   } else {
     // ================= epilogue =================
+    // Two groups of 4 warps, each covering all 128 rows of the tile.  A group owns BN/2 columns = kCPG 64-column chunk
+    // buffers per tile, fills them, syncs once among its 128 threads and issues its TMA stores as one bulk group; the two
+    // groups never wait for each other (BN = 64: they fill the two halves of ONE chunk buffer and share a barrier).
     const int te = threadIdx.x - 64;           // 0..255
     const int quarter = warp & 3;              // TMEM lanes 32*quarter .. +31
-    const int half = (warp - 2) >> 2;          // which 32 columns of each 64-column chunk
+    const int group = (warp - 2) >> 2;
+    const int tg = te & 127;
     const int rt = quarter * 32 + lane;        // row inside the tile
     const uint32_t swz = (uint32_t)(rt & 7);
+    constexpr bool kShared = BN == 64;
+    constexpr int kCPG = kShared ? 1 : BN / 128;
+    constexpr int kSets = kCBufs / C::kChunks;  // consecutive tiles whose staging buffers are disjoint
+    const bool storer = kShared ? te == 0 : tg == 0;
     const float* p_colsum = e.ln_colsum != nullptr ? e.ln_colsum : g_zeros;
     const float* p_bias = e.bias != nullptr ? e.bias : g_zeros;
     const float* p_colscale = e.colscale != nullptr ? e.colscale : g_ones;
-    uint32_t tcount = 0, cc = 0;  // tiles and 64-column chunks processed by this CTA
+    auto group_sync = [&]() {
+      if (kShared) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else if (group == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
+    };
+    uint32_t tcount = 0;  // tiles processed by this CTA; tile t stages into buffer set t % kSets
     // row statistics of the folded LayerNorm: fetched one tile ahead so that the load never sits on the critical path
     auto load_stats = [&](int tile_) -> float2 {
-      const long long row_ = (long long)(tile_ / g.n_tiles) * BM + rt;
+      const long long row_ = ((long long)(tile_ / g.n_tiles) * kCtas + cta_rank) * BM + rt;
       if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return make_float2(0.0f, 0.0f);
       return __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row_);
     };
-    float2 st_next = load_stats(blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-      const int m0 = (tile / g.n_tiles) * BM, n0 = (tile % g.n_tiles) * BN;
+    float2 st_next = load_stats(cta_tile0);
+    for (int tile = cta_tile0; tile < total_tiles; tile += cta_tile_step, ++tcount) {
+      const int m0 = ((tile / g.n_tiles) * kCtas + (int)cta_rank) * BM, n0 = (tile % g.n_tiles) * BN;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       const int row = m0 + rt;
+      const int nvalid = min(C::kChunks, (g.N - n0 + 63) >> 6);   // chunk buffers this tile fills
+      const uint32_t bset = (tcount % kSets) * C::kChunks;         // first buffer of this tile's set
       int pq0 = 0, pp0 = 0, pn0 = 0;  // patch tile origin (output column, row, image)
       if (g.conv == 2) {
         const int mt = tile / g.n_tiles;
@@ -444,109 +652,121 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float rstd = 1.0f, nmr = 0.0f;  // 1/sigma and -mean/sigma of this row (identity without a folded LayerNorm)
       if (e.ln_stats != nullptr) {
         const float2 st = st_next;
-        st_next = load_stats(tile + gridDim.x);
+        st_next = load_stats(tile + cta_tile_step);
         const float inv = 1.0f / (float)e.ln_cols;
         const float mean = st.x * inv;
         rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.0f) + e.ln_eps);
         nmr = -mean * rstd;
       }
-      mbar_wait(&tfull_bar[as], aph);
+      const float* gate_row = e.row_gate != nullptr ? e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N : nullptr;
+      if (kPair) mbar_wait_spin(&tfull_bar[as], aph);
+      else mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
-      float rs_sum = 0.0f, rs_sq = 0.0f;
-#pragma unroll 1
-      for (int j = 0; j < C::kChunks; ++j, ++cc) {
-        if (n0 + j * 64 >= g.N) break;  // uniform
-        const uint32_t b = cc % kCBufs;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + j * 64 + half * 32), r);
-        if (j == C::kChunks - 1 || n0 + (j + 1) * 64 >= g.N) {
-          // last TMEM read of this accumulator stage: hand it back to the MMA warp before the math
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 5] = clock64();
+
+      // ---- staging buffers of this tile must have been read out by the stores that last used them
+      if (storer) {
+        if (kSets >= 2 && has_res) {
+          // every store issued so far is done: the previous tile's buffers are free for the tile AFTER this one, whose
+          // residual the producer can now fetch while this epilogue runs
+          tma_store_wait_read_all();
+          if (tcount > 0) {
+            const uint32_t pset = ((tcount - 1) % kSets) * C::kChunks;
+            for (int j = 0; j < C::kChunks; ++j)
+              if (kShared || j / kCPG == group) mbar_arrive(&cfree_bar[pset + j]);
+          }
+        } else if (kSets >= 2) {
+          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSets - 1) : "memory");
+        } else {
+          tma_store_wait_read_all();
         }
-        if (has_res) mbar_wait(&rfull_bar[b], (cc / kCBufs) & 1);
+      }
+      if (!has_res) group_sync();   // (with a residual the wait on its arrival below orders the buffer reuse)
+
+      float rs_sum = 0.0f, rs_sq = 0.0f;
+      // chunks of this group; the warp's last TMEM read of the tile hands the accumulator stage back to the MMA warp
+      const int j_first = kShared ? 0 : group * kCPG;
+      const int j_last = min(kShared ? 0 : group * kCPG + kCPG - 1, nvalid - 1);
+      auto release_tmem = [&]() {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[as]), 0));  // the leader's MMA warp waits for both
+          else mbar_arrive(&tempty_bar[as]);
+        }
+      };
+      if (j_last < j_first) release_tmem();   // nothing to read for this group (narrow N)
+      if (has_res) {
+        // chunks of this group that a ragged last N tile leaves empty still take part in the residual handshake: wait
+        // for the producer's (data-less) arrival, otherwise this group could free the buffer a second time before the
+        // producer has consumed the first release and the barrier phases would alias
+        for (int j = max(j_last + 1, j_first); j <= (kShared ? 0 : group * kCPG + kCPG - 1); ++j)
+          mbar_wait(&rfull_bar[bset + (uint32_t)j], (tcount / kSets) & 1);
+      }
+#pragma unroll 1
+      for (int j = j_first; j <= j_last; ++j) {
+        const uint32_t b = bset + (uint32_t)j;
         uint8_t* cbase = cbuf + b * kCBufBytes;
         uint8_t* crow = cbase + rt * 128;
-        const int nb = n0 + j * 64 + half * 32;
-        if (g.mode != EPI_GENERIC) {
-          const uint32_t c16 = (uint32_t)(half * 4);
+        bool res_ready = !has_res;
+#pragma unroll 1
+        for (int hh = (kShared ? group : 0); hh < (kShared ? group + 1 : 2); ++hh) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + j * 64 + hh * 32), r);
+          if (j == j_last && hh == (kShared ? group : 1)) release_tmem();
+          if (!res_ready) {
+            mbar_wait(&rfull_bar[b], (tcount / kSets) & 1);
+            res_ready = true;
+          }
+          const int nb = n0 + j * 64 + hh * 32;
+          const uint32_t c16 = (uint32_t)(hh * 4);
           switch (g.mode) {
             case EPI_NONE: epi_row32<EPI_NONE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_RELU: epi_row32<EPI_RELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_GELU: epi_row32<EPI_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_SE:
-              epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq,
-                                e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N);
+            case EPI_SE: epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq, gate_row); break;
+            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            default:
+              epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, rs_sum, rs_sq);
               break;
-            default: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-          }
-        } else
-#pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          const int n = nb + q8 * 8;
-          if (n >= g.N) break;  // N % 8 == 0: a group of 8 columns is entirely inside or outside
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[q8 * 8 + i]);
-          switch (e.act) {
-            case ACT_RELU: epi_group<ACT_RELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
-            case ACT_GELU: epi_group<ACT_GELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
-            case ACT_SIGMOID: epi_group<ACT_SIGMOID>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
-            default: epi_group<ACT_NONE>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
-          }
-          uint4* cp = reinterpret_cast<uint4*>(crow + ((((uint32_t)(half * 4 + q8)) ^ swz) << 4));
-          if (has_res) {
-            const uint4 u = *cp;
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              v[2 * t] += __uint_as_float(w[t] << 16);
-              v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
-            }
-          }
-          if (e.out_bf16 != nullptr) {
-            uint32_t w[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
-              w[t] = *reinterpret_cast<const uint32_t*>(&h2);
-              const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
-              rs_sum += lo + hi;
-              rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
-            }
-            *cp = make_uint4(w[0], w[1], w[2], w[3]);
-          } else if (row < g.M) {
-            float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
-            op[0] = make_float4(v[0], v[1], v[2], v[3]);
-            op[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
-        // The chunk is staged.  Before the barrier the storing thread also makes sure that the buffer the NEXT chunk
-        // will use is free: the TMA store issued kCBufs - 1 chunks ago has finished reading it.
-        fence_async_smem();
-        if (te == 0) {
-          asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCBufs - 2) : "memory");
-          if (has_res && cc + 1 >= kCBufs) mbar_arrive(&cfree_bar[(cc + 1) % kCBufs]);
-        }
-        epi_bar_sync();
-        if (te == 0 && e.out_bf16 != nullptr) {
+      }
+      // ---- the group's chunks are staged: one fence, one barrier, its stores as one bulk group
+      fence_async_smem();
+      group_sync();
+      if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 9] = clock64();
+      if (storer && e.out_bf16 != nullptr) {
+        for (int j = j_first; j <= j_last; ++j) {
+          const uint8_t* cbase = cbuf + (bset + (uint32_t)j) * kCBufBytes;
           if (g.conv == 2) tma_store_4d(&tmC, cbase, n0 + j * 64, pq0, pp0, pn0);
           else tma_store_2d(&tmC, cbase, n0 + j * 64, m0);
-          tma_store_commit();
         }
-        if (e.gap != nullptr && g.conv == 2) {
-          // patch tile: row r = ((image, patch row, patch column)); rows outside the map / batch are skipped
-          const int cpair = te & 31, rq = te >> 5;
+        tma_store_commit();
+      }
+      if (storer && has_res && kSets < 2) {
+        // the next tile reuses these very buffers: its residual can only be fetched once the stores have read them
+        tma_store_wait_read_all();
+        for (int j = 0; j < C::kChunks; ++j)
+          if (kShared || j / kCPG == group) mbar_arrive(&cfree_bar[bset + j]);
+      }
+      if (e.gap != nullptr) {
+        // column sums of the staged bf16 chunks (split at image boundaries): thread -> 2 columns x kGapRows rows
+        constexpr int kGapRows = kShared ? 16 : 32;
+        const int cpair = te & 31, rq = kShared ? te >> 5 : tg >> 5;
+        for (int j = j_first; j <= j_last; ++j) {
+          const uint8_t* cbase = cbuf + (bset + (uint32_t)j) * kCBufBytes;
           const int n = n0 + j * 64 + cpair * 2;
-          if (n < g.N) {
+          if (n >= g.N) continue;
+          float s0 = 0.0f, s1 = 0.0f;
+          if (g.conv == 2) {
+            // patch tile: row rr = ((image, patch row, patch column)); rows outside the map / batch are skipped
             const int per_img = g.bw * g.bh;
-            float s0 = 0.0f, s1 = 0.0f;
             int cur = -1;
-            for (int k = 0; k < 16; ++k) {
-              const int rr = rq * 16 + k;
+            for (int k = 0; k < kGapRows; ++k) {
+              const int rr = rq * kGapRows + k;
               if (rr >= g.prow) break;
               const int ni = rr / per_img, rem = rr - ni * per_img;
               const int py = rem / g.bw, px = rem - py * g.bw;
@@ -568,18 +788,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
               atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
             }
-          }
-        } else
-        if (e.gap != nullptr) {
-          // column sums of the staged bf16 chunk, split at image boundaries: thread -> (2 columns, 16 rows)
-          const int cpair = te & 31, rq = te >> 5;
-          const int n = n0 + j * 64 + cpair * 2;
-          if (n < g.N && m0 + rq * 16 < g.M) {
-            int rr = rq * 16;
+          } else if (m0 + rq * kGapRows < g.M) {
+            int rr = rq * kGapRows;
             int img = (m0 + rr) / e.gap_rows;
             int next = (img + 1) * e.gap_rows - m0;  // first tile row of the next image
-            float s0 = 0.0f, s1 = 0.0f;
-            for (int k = 0; k < 16; ++k, ++rr) {
+            for (int k = 0; k < kGapRows; ++k, ++rr) {
               if (m0 + rr >= g.M) break;
               if (rr == next) {
                 atomicAdd(e.gap + (size_t)img * g.N + n, s0);
@@ -598,18 +811,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      if (e.row_stats != nullptr && row < g.M) {
+      if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 6] = clock64();
+      if (e.row_stats != nullptr && row < g.M && j_last >= j_first) {
         atomicAdd(e.row_stats + 2 * (size_t)row, rs_sum);
         atomicAdd(e.row_stats + 2 * (size_t)row + 1, rs_sq);
       }
     }
-    if (te == 0) tma_store_wait_all();
+    if (storer) tma_store_wait_all();
+
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // no CTA of the pair leaves (or frees TMEM) while the other may still reach into it
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
   }
 }
 
@@ -701,20 +918,38 @@ int ensure_neutral(cudaStream_t st) {
   return VIP_OK;
 }
 
-template <int BN, bool kDeep>
+template <int BN, bool kDeep, bool kPair = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
            const GemmArgs& g, cudaStream_t st) {
-  using C = Cfg<BN, kDeep>;
-  auto kern = gemm_tcgen05_kernel<BN, kDeep>;
+  using C = Cfg<BN, kDeep, kPair>;
+  auto kern = gemm_tcgen05_kernel<BN, kDeep, kPair>;
   static bool configured = false;  // per-process; attribute is per-function
   if (!configured) {
     VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
     configured = true;
   }
   const int tiles = g.m_tiles * g.n_tiles;
-  const int slots = num_sms() * C::kMinBlocks;
-  const int grid = tiles < slots ? tiles : slots;
-  kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
+  const int ctas_per_tile = kPair ? 2 : 1;
+  int slots = num_sms() * C::kMinBlocks / ctas_per_tile;
+  const int grid = (tiles < slots ? tiles : slots) * ctas_per_tile;
+  static const bool cluster_test = [] { const char* v = getenv("VIP_GEMM_CLUSTER_TEST"); return v != nullptr && v[0] == '1'; }();
+  if (kPair || (cluster_test && grid % 2 == 0)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VIP_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, g));
+  } else {
+    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
+  }
   VIP_CUDA(cudaGetLastError());
   count_launch();
   return VIP_OK;
@@ -782,9 +1017,15 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   int rc0 = ensure_neutral(stream);
   if (rc0 != VIP_OK) return rc0;
   const bool deep = g.num_kb > 4;  // K > 256: the MMA loop dominates; otherwise the epilogue does
-  const int bn = pick_bn(M, N, deep, g.conv == 1, g.num_kb);
+  int bn = pick_bn(M, N, deep, g.conv == 1, g.num_kb);
+  // pair mode (two CTAs, tcgen05.mma.cta_group::2, 256-row tiles) for the plain deep GEMMs; VIP_GEMM_PAIR=0 disables
+  static const bool pair_env = [] { const char* v = getenv("VIP_GEMM_PAIR"); return v == nullptr || v[0] != '0'; }();
+  // Measured (profiles/README.md): 76 % of the cuBLAS peak at 8192^3 against 71 % for one CTA per tile, but no gain below
+  // K ~ 4096, where the tile prologue and the epilogue dominate: enabled for long K loops only.
+  const bool pair = pair_env && deep && g.conv == 0 && M >= 2 * BM && N >= 128 && g.num_kb >= 64;
+  if (pair && bn < 128) bn = 128;
   CUtensorMap tmB, tmC, tmR;
-  int rc = make_tmap_2d(&tmB, B, N, K, ldb, bn);
+  int rc = make_tmap_2d(&tmB, B, N, K, ldb, pair ? bn / 2 : bn);
   if (rc != VIP_OK) return rc;
   tmC = tmB;
   tmR = tmB;
@@ -799,21 +1040,61 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
     if (rc != VIP_OK) return rc;
   }
   g.mode = pick_mode(epi);
+  g.trace = nullptr;
+  {
+    static const int dbg_env = [] { const char* v = getenv("VIP_GEMM_DEBUG"); return v != nullptr ? atoi(v) : 0; }();
+    g.dbg = dbg_env;
+  }
+  static const bool trace_env = [] { const char* v = getenv("VIP_GEMM_TRACE"); return v != nullptr && v[0] == '1'; }();
+  long long* trace_dev = nullptr;
+  const int trace_tiles = 2048;
+  if (trace_env) {
+    if (cudaMalloc(&trace_dev, trace_tiles * 16 * sizeof(long long)) == cudaSuccess) {
+      cudaMemsetAsync(trace_dev, 0, trace_tiles * 16 * sizeof(long long), stream);
+      g.trace = trace_dev;
+    }
+  }
   g.M = (int)M;
   g.N = N;
   g.K = K;
-  g.m_tiles = (int)((M + BM - 1) / BM);
+  g.m_tiles = pair ? (int)((M + 2 * BM - 1) / (2 * BM)) : (int)((M + BM - 1) / BM);
   g.n_tiles = (N + bn - 1) / bn;
   g.epi = epi;
-  if (deep) {
+  int lrc;
+  if (pair) {
+    lrc = bn == 256 ? launch<256, true, true>(tmA, tmB, tmC, tmR, g, stream) : launch<128, true, true>(tmA, tmB, tmC, tmR, g, stream);
+  } else if (deep) {
     switch (bn) {
-      case 256: return launch<256, true>(tmA, tmB, tmC, tmR, g, stream);
-      case 128: return launch<128, true>(tmA, tmB, tmC, tmR, g, stream);
-      default: return launch<64, true>(tmA, tmB, tmC, tmR, g, stream);
+      case 256: lrc = launch<256, true>(tmA, tmB, tmC, tmR, g, stream); break;
+      case 128: lrc = launch<128, true>(tmA, tmB, tmC, tmR, g, stream); break;
+      default: lrc = launch<64, true>(tmA, tmB, tmC, tmR, g, stream); break;
     }
+  } else if (bn == 128) {
+    lrc = launch<128, false>(tmA, tmB, tmC, tmR, g, stream);
+  } else {
+    lrc = launch<64, false>(tmA, tmB, tmC, tmR, g, stream);
   }
-  if (bn == 128) return launch<128, false>(tmA, tmB, tmC, tmR, g, stream);
-  return launch<64, false>(tmA, tmB, tmC, tmR, g, stream);
+  if (trace_dev != nullptr) {
+    // experiment aid: timeline of CTA 0 (cycles relative to its first stamp)
+    static int printed = 0;
+    cudaStreamSynchronize(stream);
+    if (printed < 2) {
+      ++printed;
+      static long long h[2048 * 16];
+      cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+      const long long t0 = h[0];
+      fprintf(stderr, "gemm trace M=%lld N=%d K=%d bn=%d deep=%d mode=%d conv=%d: tile | load-issue begin end | mma tmem-free first-full commit | epi begin end\n",
+              M, N, K, bn, (int)deep, g.mode, g.conv);
+      for (int t = 0; t < 24 && h[t * 16] != 0; ++t) {
+        const long long* q = h + t * 16;
+        fprintf(stderr, "  %3d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld | chunk0: ld+%lld math+%lld fence+%lld wait+%lld bar+%lld\n", t,
+                q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[8] - q[5], q[9] - q[8],
+                q[10] - q[9], q[11] - q[10], q[12] - q[11]);
+      }
+    }
+    cudaFree(trace_dev);
+  }
+  return lrc;
 }
 
 }  // namespace
