@@ -27,7 +27,6 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int kThreads = 320;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kCBufBytes = BM * 128;  // 128 rows x 64 bf16
 constexpr int kMaxCols = 8192;        // widest N the neutral-parameter vectors cover
@@ -268,6 +267,9 @@ struct Cfg {
   static constexpr int kCBufs = kDeep ? 4 : 2;   // ring of output staging buffers (one 64-column chunk each)
   static constexpr int kMinBlocks = kDeep ? 1 : 2;
   static constexpr int kChunks = BN / 64;   // 64-column chunks per tile
+  // epilogue groups of 4 warps (each covers all 128 rows): one per chunk for the 256-wide deep tiles, otherwise two
+  static constexpr int kGroups = (kDeep && BN == 256) ? 4 : 2;
+  static constexpr int kThreads = 64 + 128 * kGroups;
   static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: a power of two
   static constexpr int kSmem = kStages * kStageBytes + kCBufs * kCBufBytes + 1024 + 256;
   static_assert(kDeep || BN <= 128, "two CTAs per SM need at most 256 TMEM columns each");
@@ -416,7 +418,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
 }
 
 template <int BN, bool kDeep, bool kPair = false>
-__global__ void __launch_bounds__(kThreads, Cfg<BN, kDeep, kPair>::kMinBlocks)
+__global__ void __launch_bounds__(Cfg<BN, kDeep, kPair>::kThreads, Cfg<BN, kDeep, kPair>::kMinBlocks)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
   using C = Cfg<BN, kDeep, kPair>;
@@ -454,7 +456,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8 * kCtas);  // one arrival per epilogue warp (of both CTAs in pair mode)
+      mbar_init(&tempty_bar[s], 4 * C::kGroups * kCtas);  // one arrival per epilogue warp (of both CTAs in pair mode)
     }
     for (int b = 0; b < kCBufs; ++b) {
       mbar_init(&rfull_bar[b], 1);
@@ -609,14 +611,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Two groups of 4 warps, each covering all 128 rows of the tile.  A group owns BN/2 columns = kCPG 64-column chunk
     // buffers per tile, fills them, syncs once among its 128 threads and issues its TMA stores as one bulk group; the two
     // groups never wait for each other (BN = 64: they fill the two halves of ONE chunk buffer and share a barrier).
-    const int te = threadIdx.x - 64;           // 0..255
+    const int te = threadIdx.x - 64;           // 0 .. 128 * kGroups - 1
     const int quarter = warp & 3;              // TMEM lanes 32*quarter .. +31
     const int group = (warp - 2) >> 2;
     const int tg = te & 127;
     const int rt = quarter * 32 + lane;        // row inside the tile
     const uint32_t swz = (uint32_t)(rt & 7);
     constexpr bool kShared = BN == 64;
-    constexpr int kCPG = kShared ? 1 : BN / 128;
+    constexpr int kCPG = kShared ? 1 : C::kChunks / C::kGroups;
     constexpr int kSets = kCBufs / C::kChunks;  // consecutive tiles whose staging buffers are disjoint
     const bool storer = kShared ? te == 0 : tg == 0;
     const float* p_colsum = e.ln_colsum != nullptr ? e.ln_colsum : g_zeros;
@@ -624,8 +626,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const float* p_colscale = e.colscale != nullptr ? e.colscale : g_ones;
     auto group_sync = [&]() {
       if (kShared) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else if (group == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
-      else asm volatile("bar.sync 3, 128;" ::: "memory");
+      else asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
     };
     uint32_t tcount = 0;  // tiles processed by this CTA; tile t stages into buffer set t % kSets
     // row statistics of the folded LayerNorm: fetched one tile ahead so that the load never sits on the critical path
@@ -936,7 +937,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   if (kPair || (cluster_test && grid % 2 == 0)) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(C::kThreads);
     cfg.dynamicSmemBytes = C::kSmem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -948,7 +949,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     cfg.numAttrs = 1;
     VIP_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, g));
   } else {
-    kern<<<grid, kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
+    kern<<<grid, C::kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
   }
   VIP_CUDA(cudaGetLastError());
   count_launch();
@@ -1022,7 +1023,8 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   static const bool pair_env = [] { const char* v = getenv("VIP_GEMM_PAIR"); return v == nullptr || v[0] != '0'; }();
   // Measured (profiles/README.md): 76 % of the cuBLAS peak at 8192^3 against 71 % for one CTA per tile, but no gain below
   // K ~ 4096, where the tile prologue and the epilogue dominate: enabled for long K loops only.
-  const bool pair = pair_env && deep && g.conv == 0 && M >= 2 * BM && N >= 128 && g.num_kb >= 64;
+  static const int pair_min_kb = [] { const char* v = getenv("VIP_GEMM_PAIR_MIN_KB"); return v != nullptr ? atoi(v) : 64; }();
+  const bool pair = pair_env && deep && g.conv == 0 && M >= 2 * BM && N >= 128 && g.num_kb >= pair_min_kb;
   if (pair && bn < 128) bn = 128;
   CUtensorMap tmB, tmC, tmR;
   int rc = make_tmap_2d(&tmB, B, N, K, ldb, pair ? bn / 2 : bn);
