@@ -151,8 +151,11 @@ int vip_scale_add_act_bf16(const void* y, const float* gate, const void* shortcu
  * next contraction. */
 int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats, long long M,
                        int C, float eps, void* cuda_stream);
-/* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ exact GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134 */
-int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, int W, int C, int gelu, void* cuda_stream);
+/* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134.
+ * gap (f32 [N,C] or NULL, zeroed by the caller) accumulates the per-image channel sums of the output: the SE squeeze
+ * (GlobalAveragePooling, feature.py:55) without a second pass over the map. */
+int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, float* gap, int N, int H, int W, int C, int gelu,
+                       void* cuda_stream);
 /* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
 int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
 /* Window attention, head_dim 32, window partition/reverse folded into addressing: gcvit attention.py:52-83, window.py:3-14.

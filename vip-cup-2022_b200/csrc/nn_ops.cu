@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 // (image, column, 8-channel group) and walks down the rows with the 3x3 window and the 72 weights in registers, so every
 // input element is fetched three times (once per neighbouring column) instead of nine.
 __global__ void __launch_bounds__(128) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[3][3][C]*/,
-                                                        bf16* __restrict__ out, int N, int H, int W, int C, int gelu) {
+                                                        bf16* __restrict__ out, float* __restrict__ gap /*[N][C] or null*/,
+                                                        int N, int H, int W, int C, int gelu) {
   const int c8n = C >> 3;
   const long long total = (long long)N * W * c8n;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const bf16* __restrict__
     for (int k = 0; k < 8; ++k) win[0][dx][k] = 0.0f;
   load_row(0, win[1]);
   bf16* op = out + (long long)n * H * W * C + (long long)ox * C + c8 * 8;
+  float colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // of the rounded outputs of this column (SE squeeze, feature.py:55)
   for (int y = 0; y < H; ++y) {
     load_row(y + 1, win[2]);
     float acc[8];
@@ -357,7 +359,14 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const bf16* __restrict__
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = gelu_erf(acc[k]);
     }
-    *reinterpret_cast<bf16x8*>(op + (long long)y * W * C) = pack8(acc);
+    const bf16x8 pk = pack8(acc);
+    *reinterpret_cast<bf16x8*>(op + (long long)y * W * C) = pk;
+    if (gap != nullptr) {
+      float r8[8];
+      unpack8(pk, r8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) colsum[k] += r8[k];
+    }
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
@@ -365,6 +374,10 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const bf16* __restrict__
         win[0][dx][k] = win[1][dx][k];
         win[1][dx][k] = win[2][dx][k];
       }
+  }
+  if (gap != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(gap + (long long)n * C + c8 * 8 + k, colsum[k]);
   }
 }
 
@@ -526,11 +539,12 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int N, int H, int W, int C, int gelu,
+extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, float* gap, int N, int H, int W, int C, int gelu,
                                   void* stream) {
   VIP_REQUIRE(x && out && w && C % 8 == 0, VIP_ERR_INVALID, "vip_dwconv3x3_bf16: bad argument");
   const long long threads = (long long)N * W * (C / 8);
-  dwconv3x3_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ST(stream)>>>((const bf16*)x, w, (bf16*)out, N, H, W, C, gelu);
+  dwconv3x3_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ST(stream)>>>((const bf16*)x, w, (bf16*)out, gap, N, H, W, C,
+                                                                             gelu);
   LAUNCH_CHECK();
 }
 

@@ -210,8 +210,9 @@ class GCViT:
     def _mb_apply(self, x, d):
         """x + [pad1 -> DW3x3 -> GELU -> SE -> Conv1x1](x)   (feature.py:105-109,144-150)"""
         b, h, w, c = x.shape
-        y = nn.dwconv3x3(x, d["dw"], gelu=True)
-        pooled, _ = nn.global_avgpool(y)
+        gap = nn.zero_(torch.empty((b, c), dtype=torch.float32, device=x.device))
+        y = nn.dwconv3x3(x, d["dw"], gelu=True, gap=gap)        # SE squeeze accumulated by the same kernel
+        pooled = nn.scale_cast_bf16(gap, 1.0 / (h * w))
         hid = nn.gemm(pooled, d["fc0"], act="gelu")
         gate = nn.gemm(hid, d["fc2"], act="sigmoid", out_dtype=torch.float32)
         y = nn.scale_add_act(y, gate, None, out=y)

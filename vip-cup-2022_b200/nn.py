@@ -134,11 +134,13 @@ def layernorm(x, gamma, beta, eps=1e-5, row_stats=None):
     return out
 
 
-def dwconv3x3(x, w, gelu=False):
-    _chk(x, "x"), _chk(w, "w", torch.float32)
+def dwconv3x3(x, w, gelu=False, gap=None):
+    """gap: f32 [N,C] zeroed accumulator that receives the per-image channel sums of the output (fused SE squeeze)."""
+    _chk(x, "x"), _chk(w, "w", torch.float32), _chk(gap, "gap", torch.float32)
     n, h, wd, c = x.shape
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().vip_dwconv3x3_bf16(_p(x), _p(w), _p(out), n, h, wd, c, int(gelu), _st()), "vip_dwconv3x3_bf16")
+    _lib.check(_lib.lib().vip_dwconv3x3_bf16(_p(x), _p(w), _p(out), _p(gap), n, h, wd, c, int(gelu), _st()),
+               "vip_dwconv3x3_bf16")
     return out
 
 
