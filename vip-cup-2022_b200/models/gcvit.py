@@ -182,6 +182,7 @@ class GCViT:
     def load_weights(self, W: dict):
         cfg, p = self.cfg, {}
         p["proj"] = self._conv3(W, "patch_embed/proj", bias=True)
+        p["proj_pair"] = nn.pair_rows_weights(*p["proj"])
         p["conv_down"] = self._reduce(W, "patch_embed/conv_down")
         for i, depth in enumerate(cfg["depths"]):
             ws, heads = cfg["window_size"][i], cfg["num_heads"][i]
@@ -242,7 +243,10 @@ class GCViT:
         p, cfg = self.p, self.cfg
         if p is None:
             raise RuntimeError("load_weights() first")
-        x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
+        if (x.shape[0] * ((x.shape[1] - 1) // 2 + 1) * ((x.shape[2] - 1) // 2 + 1)) % 2 == 0 and p["proj"][0].shape[1] == 32:
+            x = nn.conv2d_paired(x, *p["proj_pair"], ksize=3, stride=2, pad=1)
+        else:
+            x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
         nimg = x.shape[0]
 
         def level_stats(i, tokens):  # one zeroed arena per level: [1 + 2*depth, tokens, 2]

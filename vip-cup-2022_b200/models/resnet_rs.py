@@ -42,6 +42,21 @@ def _fold_conv_bn(W, conv, bnorm, device):
             torch.from_numpy(b - m * s).to(device).contiguous())
 
 
+def _pair_columns(w, bias, cin, cout):
+    """3x3 stride-1 'same' convolution on [H, W, cin] restated on horizontal pixel PAIRS: input [H, W/2, 2 cin], output
+    [H, W/2, 2 cout] (the same memory as [H, W, cout]).  With cin = 32 a 64-channel k-block of the implicit GEMM is then
+    full instead of half zero-filled and the number of output tiles halves, which is what bounds these memory-heavy
+    stem layers (stem_conv_2/3, resnet_rs_model.py:104-123).  w: bf16-to-be f32 [cout, 9*cin] in (r, s, c) order."""
+    w = w.reshape(cout, 3, 3, cin)
+    wp = np.zeros((2, cout, 3, 3, 2, cin), np.float32)            # [dxo, co, r, sxs, half, ci]
+    for dxo in range(2):
+        for s in range(3):                                        # original tap s - 1 in {-1, 0, 1}
+            off = dxo + s - 1                                     # input pixel offset from the pair's first pixel
+            sxs, half = off // 2, off % 2                         # pair offset in {-1, 0, 1}, pixel inside that pair
+            wp[dxo, :, :, sxs + 1, half, :] = w[:, :, s, :]
+    return wp.reshape(2 * cout, 9 * 2 * cin), np.concatenate([bias, bias])
+
+
 def _dense(W, name, device):
     k = np.asarray(W[name + "/kernel"], np.float32)
     k = k.reshape(-1, k.shape[-1])  # (1,1,Cin,Cout) -> (Cin,Cout)
@@ -125,6 +140,11 @@ class ResNetRS:
         d, p = self.device, {}
         for i in range(1, 5):
             p[f"stem{i}"] = _fold_conv_bn(W, f"stem_conv_{i}", f"stem_batch_norm_{i}", d)
+        p["stem1_pair"] = nn.pair_rows_weights(*p["stem1"])
+        for i in (2, 3):   # 32-channel inputs: pixel-pair form (see _pair_columns); used when the map width is even
+            wt, bias = p[f"stem{i}"]
+            w2, b2 = _pair_columns(wt.float().cpu().numpy(), bias.cpu().numpy(), 32, wt.shape[0])
+            p[f"stem{i}_pair"] = (torch.from_numpy(w2).to(d).to(torch.bfloat16).contiguous(), torch.from_numpy(b2).to(d).contiguous())
         for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
             for bi in range(reps):
                 n = f"c{gi + 2}_block_{bi}_"
@@ -161,7 +181,14 @@ class ResNetRS:
         if p is None:
             raise RuntimeError("load_weights() first")
         for i, s in ((1, self.first_strides), (2, 1), (3, 1), (4, 2)):
-            x = nn.conv2d(x, *p[f"stem{i}"], ksize=3, stride=s, pad=1, act="relu")
+            n, h, w, c = x.shape
+            if i == 1 and c == 3 and (n * ((h - 1) // s + 1) * ((w - 1) // s + 1)) % 2 == 0:
+                x = nn.conv2d_paired(x, *p["stem1_pair"], ksize=3, stride=s, pad=1, act="relu")
+            elif f"stem{i}_pair" in p and w % 2 == 0 and c == 32:
+                y = nn.conv2d(x.view(n, h, w // 2, 2 * c), *p[f"stem{i}_pair"], ksize=3, stride=1, pad=1, act="relu")
+                x = y.view(n, h, w, -1)
+            else:
+                x = nn.conv2d(x, *p[f"stem{i}"], ksize=3, stride=s, pad=1, act="relu")
         if taps is not None:
             taps["stem"] = x
         nimg = x.shape[0]

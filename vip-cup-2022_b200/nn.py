@@ -88,6 +88,32 @@ def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, *
     return y.view(n, ho, wo, cout)
 
 
+def pair_rows_weights(w, bias):
+    """For ``conv2d_paired``: [Cout, 32] (K padded to 32) -> block-diagonal bf16 [2 Cout, 64] and the duplicated bias."""
+    cout, kp = w.shape
+    w2 = torch.zeros((2 * cout, 2 * kp), dtype=w.dtype, device=w.device)
+    w2[:cout, :kp] = w
+    w2[cout:, kp:] = w
+    return w2.contiguous(), (None if bias is None else torch.cat([bias, bias]).contiguous())
+
+
+def conv2d_paired(x, w_pair, bias_pair, ksize, stride, pad, act=None):
+    """Small-Cin convolution (the 3-channel network input): explicit im2col rows of 32, then TWO output pixels per GEMM row
+    (the [M, 32] matrix viewed as [M/2, 64], block-diagonal weights): full 64-wide k-blocks and half as many tiles."""
+    _chk(x, "x"), _chk(w_pair, "w_pair")
+    n, h, wd, c = x.shape
+    ho = (h + 2 * pad - ksize) // stride + 1
+    wo = (wd + 2 * pad - ksize) // stride + 1
+    kp, cout = w_pair.shape[1] // 2, w_pair.shape[0] // 2
+    m = n * ho * wo
+    if m % 2:
+        raise VipError("conv2d_paired needs an even number of output pixels")
+    a = torch.empty((m, kp), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_im2col_bf16(_p(x), n, h, wd, c, ksize, stride, pad, ho, wo, _p(a), kp, _st()), "vip_im2col_bf16")
+    y = gemm(a.view(m // 2, 2 * kp), w_pair, bias=bias_pair, act=act)
+    return y.view(n, ho, wo, cout)
+
+
 def zero_(t):
     """cudaMemsetAsync(0) on the current stream (accumulators of the fused row-statistics / pooling epilogues)."""
     _lib.check(_lib.lib().vip_memset_async(_p(t), 0, t.numel() * t.element_size(), _st()), "vip_memset_async")
