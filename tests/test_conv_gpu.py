@@ -29,3 +29,18 @@ def test_conv3x3_matches_torch(cuda_device, n, h, c, cout, stride):
     assert out.shape == ref.shape
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_conv3x3_patch_tiles_in_child_process(cuda_device):
+    """The tiled-4-D ("patch" tile) feed of the implicit GEMM is selected by VIP_CONV_PATCH=1, read once per process:
+    run three shapes of the main test in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("VIP_CONV_PATCH") == "1":
+        pytest.skip("already in the child")
+    env = dict(os.environ, VIP_CONV_PATCH="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k", "matches_torch and (2-50-64 or 2-25-256 or 2-56-96)"],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]

@@ -88,3 +88,42 @@ def test_gemm_fused_global_average_pool(cuda_device, nimg, hw, n, k):
     ref = out.float().view(nimg, hw, n).sum(1)
     assert torch.allclose(gap, ref, rtol=1e-3, atol=1e-2 * hw ** 0.5), (gap - ref).abs().max().item()
     assert (out.float() - a.float() @ b.float().t()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("nimg,hw,n,k", [(3, 49, 256, 64), (5, 169, 1024, 256), (2, 2500, 256, 64), (6, 49, 2048, 512)])
+def test_gemm_se_tail_epilogue(cuda_device, nimg, hw, n, k):
+    """SE bottleneck tail fused into the contraction: relu((acc + bias) * gate[image] + shortcut)
+    (models/resnet_rs/resnet_rs_model.py:183,278-280)."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(nimg * hw + n + k)
+    a = (torch.randn(nimg * hw, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    b = (torch.randn(n, k, generator=g) * 0.3).to(torch.bfloat16).to(cuda_device)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    gate = torch.rand(nimg, n, generator=g).to(cuda_device)
+    res = torch.randn(nimg * hw, n, generator=g).to(torch.bfloat16).to(cuda_device)
+    out = nn.gemm(a, b, bias=bias, act="relu", residual=res, row_gate=gate, gate_rows=hw)
+    ref = torch.relu((a.float() @ b.float().t() + bias) * gate.repeat_interleave(hw, 0) + res.float())
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_dwconv_fused_squeeze(cuda_device):
+    """DepthwiseConv2D + GELU with the SE squeeze (per-image channel sums) accumulated by the same kernel."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = (torch.randn(3, 14, 14, 64, generator=g)).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn(3, 3, 64, generator=g) * 0.3).to(cuda_device)
+    gap = nn.zero_(torch.empty((3, 64), dtype=torch.float32, device=cuda_device))
+    y = nn.dwconv3x3(x, w, gelu=True, gap=gap)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.permute(2, 0, 1)[:, None], padding=1, groups=64)
+    ref = torch.nn.functional.gelu(ref).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.allclose(gap, y.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
