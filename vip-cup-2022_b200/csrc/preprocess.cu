@@ -299,7 +299,17 @@ struct FastDiv {
   __device__ __forceinline__ int div(int i) const { return d == 1 ? i : (int)__umulhi((unsigned)i, m); }
 };
 
-__device__ __forceinline__ float u8f(unsigned word, int k) { return (float)((word >> (8 * k)) & 0xffu); }
+// Exact small-integer <-> float conversions on the FMA / ALU pipes (I2F / F2I issue on the quarter-rate XU pipe and
+// there are ~0.8 M of them per image): 2^23 + n has n in its low mantissa bits for 0 <= n < 2^23.
+__device__ __forceinline__ float u8f(unsigned word, int k) {   // (float) byte k of word
+  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned)k)), 8388608.0f);
+}
+__device__ __forceinline__ float small_int_to_float(int n) {   // 0 <= n < 2^23
+  return __fsub_rn(__uint_as_float(0x4B000000u | (unsigned)n), 8388608.0f);
+}
+__device__ __forceinline__ int trunc_small_float(float x) {    // (int)x for 0 <= x < 2^22 (round toward zero = floor)
+  return (int)(__float_as_uint(__fadd_rz(x, 8388608.0f)) & 0x7fffffu);
+}
 
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
@@ -454,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
             const float f = div255(val);
             fv[dy][dx][c] = f;
             // tf.image.convert_image_dtype(float -> uint8, saturate=True): trunc(clip(f * 255.5, 0, 255))
-            rgb[c] = (int)fminf(fmaxf(__fmul_rn(f, 255.5f), 0.0f), 255.0f);
+            rgb[c] = trunc_small_float(fminf(fmaxf(__fmul_rn(f, 255.5f), 0.0f), 255.0f));
           }
           if (jpeg) {
             // jccolor.c rgb_ycc_convert
@@ -601,9 +611,9 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
           const int G = __vimin_s32_relu((-22554 * cb - 46802 * cr + (yb + 128 * (22554 + 46802))) >> 16, 255);
           const int B = __vimin_s32_relu((116130 * cb + (yb - 128 * 116130)) >> 16, 255);
           // convert_image_dtype(uint8 -> float32): cast * (1/255)
-          fv[dy][dx][0] = __fmul_rn((float)R, 0.003921568859368562698f);
-          fv[dy][dx][1] = __fmul_rn((float)G, 0.003921568859368562698f);
-          fv[dy][dx][2] = __fmul_rn((float)B, 0.003921568859368562698f);
+          fv[dy][dx][0] = __fmul_rn(small_int_to_float(R), 0.003921568859368562698f);
+          fv[dy][dx][1] = __fmul_rn(small_int_to_float(G), 0.003921568859368562698f);
+          fv[dy][dx][2] = __fmul_rn(small_int_to_float(B), 0.003921568859368562698f);
         }
       }
       emit_quad<kBf16>(dst, e0, Ho, Wo, cy, cx, flags, fv);
