@@ -35,23 +35,26 @@ def _ref(qkv, qg, table, B, H, W, C, ws, heads):
     return o
 
 
-@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("impl", ["ws", "mma", "tc"])
 @pytest.mark.parametrize("B,H,ws,heads,glob", [(2, 14, 7, 2, False), (3, 21, 7, 4, True), (2, 14, 14, 8, False),
-                                               (1, 14, 14, 3, True), (5, 7, 7, 16, False), (1, 56, 7, 2, True)])
+                                               (1, 14, 14, 3, True), (5, 7, 7, 16, False), (1, 56, 7, 2, True), (3, 14, 7, 3, False),
+                                               (2, 14, 14, 3, True), (1, 7, 7, 1, False)])
 def test_window_attention_matches_torch(cuda_device, B, H, ws, heads, glob, impl):
-    """Both implementations (attention.cu mma.sync, attention_tc.cu tcgen05/TMEM); the library reads VIP_ATTN_TCGEN05
-    once per process, so the tcgen05 kernel is exercised in a child process."""
-    if impl == "tcgen05":
-        import os
+    """All three implementations (attention_ws.cu persistent tcgen05 -- the default --, attention.cu mma.sync,
+    attention_tc.cu one-item-per-CTA tcgen05); the library reads VIP_ATTN_IMPL once per process, so the non-default
+    kernels are exercised in a child process.  Odd head counts and odd window counts cover the half-empty head pair and
+    the half-empty two-window tile of the persistent kernel."""
+    import os
+
+    if impl != os.environ.get("VIP_ATTN_IMPL", "ws"):
         import subprocess
         import sys
 
-        if os.environ.get("VIP_ATTN_TCGEN05") != "1":
-            env = dict(os.environ, VIP_ATTN_TCGEN05="1")
-            r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k",
-                                f"tcgen05 and {B}-{H}-{ws}-{heads}-{glob}"], env=env, capture_output=True, text=True)
-            assert r.returncode == 0, r.stdout[-3000:]
-            return
+        env = dict(os.environ, VIP_ATTN_IMPL=impl)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", __file__, "-k",
+                            f"{B}-{H}-{ws}-{heads}-{glob}-{impl}"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-3000:]
+        return
     import torch
 
     from vipcup_b200 import nn
