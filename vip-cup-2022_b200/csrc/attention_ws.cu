@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -127,6 +128,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+#ifdef VIP_ATTN_TRACE
+// bring-up aid (build with VIP_NVCC_EXTRA=-DVIP_ATTN_TRACE): cycle counts of the MMA issuer of group 0 in CTA 0, summed over
+// its jobs: [0] jobs, [1] QK issue -> S complete, [2] S complete -> P arrived, [3] P arrived -> O complete
+__device__ long long g_attn_trace[8];
+#endif
+
 template <int WS>
 struct WsCfg {
   static constexpr int N = WS * WS;                       // tokens of a window (49 / 196)
@@ -162,7 +169,8 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   constexpr int N = Cfg::N, WPT = Cfg::WPT, MT = Cfg::MT, QPW = Cfg::QPW, WKEYS = Cfg::WKEYS, KEYS = Cfg::KEYS;
   constexpr int TAB = Cfg::TAB, kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the array, not an integer round trip: the compiler keeps the shared address space -> LDS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage0 = smem;
   float* sT = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);      // [heads][TAB], times log2 e
   float* sTmax = sT + ((heads * TAB + 3) / 4) * 4;                               // [heads]
@@ -275,7 +283,15 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           umma_ss(tg + Cfg::S_COL, qdesc, kdesc, idesc_s, 0u);
           umma_ss(tg + Cfg::S_COL, qdesc + 2, kdesc + 2, idesc_s, 1u);
           umma_commit(s_full + g);
+#ifdef VIP_ATTN_TRACE
+          const long long t0 = clock64();
+          mbar_wait(s_full + g, job & 1u);
+          const long long t1 = clock64();
+#endif
           mbar_wait(p_full + g, job & 1u);
+#ifdef VIP_ATTN_TRACE
+          const long long t2 = clock64();
+#endif
           mbar_wait(o_free + g, (job & 1u) ^ 1u);   // O of the previous job has been read
           tc_fence_after();
 #pragma unroll
@@ -283,6 +299,16 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             umma_ts(tg + Cfg::O_COL, tg + Cfg::P_COL + 8 * k, vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
           umma_commit(o_full + g);
           if (mt == MT - 1) umma_commit(empty + s);
+#ifdef VIP_ATTN_TRACE
+          mbar_wait(o_full + g, job & 1u);
+          const long long t3 = clock64();
+          if (blockIdx.x == 0 && g == 0) {
+            g_attn_trace[0] += 1;
+            g_attn_trace[1] += t1 - t0;
+            g_attn_trace[2] += t2 - t1;
+            g_attn_trace[3] += t3 - t2;
+          }
+#endif
         }
       }
     }
@@ -324,42 +350,27 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         float lsum = 1.0f;
         if (warp_live) {
           const uint32_t srow = tl + Cfg::S_COL + jq * WKEYS;
-          // ---- pass 1: maximum of the raw scores of the row
-          float mx = -3.0e38f;
-#pragma unroll
-          for (int c = 0; c < Cfg::NCH; ++c) {
-            uint32_t r[32];
-            tmem_ld32_nowait(srow + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(r[i]));
-          }
-          // upper bound of the maximum of (scaled score + bias): softmax is exact after normalisation, no overflow
-          const float mrow = fmaf(mx, scale_log2e, tabmax);
           const float* pb = tab + (tokc / WS + WS - 1) * (2 * WS - 1) + tokc % WS + WS - 1;
-          // ---- pass 2: P = exp2(score * scale + bias - mrow), packed bf16 pairs back into TMEM
-          lsum = 0.0f;
           const uint32_t prow = tl + Cfg::P_COL + jq * (WKEYS / 2);
-#pragma unroll
-          for (int c = 0; c < Cfg::NCH; ++c) {
-            uint32_t r[32];
-            tmem_ld32_nowait(srow + c * 32, r);
-            tmem_ld_wait();
+          uint32_t r[2][32];
+          float mx = -3.0e38f, mrow;
+          float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          // P chunk c = exp2(score * scale + bias - mrow) of the 32 raw scores in `rc`, packed bf16 pairs back into TMEM
+          auto emit = [&](const int c, const uint32_t (&rc)[32]) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               float pv[2];
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int j = c * 32 + i + e;          // key = (j / WS, j % WS), compile-time
+                const int j = c * 32 + i + e;          // key = (j / WS, j % WS), compile-time after unrolling
                 if (j < N) {
-                  const float sc = fmaf(__uint_as_float(r[i + e]), scale_log2e, pb[-((j / WS) * (2 * WS - 1) + j % WS)]);
+                  const float sc = fmaf(__uint_as_float(rc[i + e]), scale_log2e, pb[-((j / WS) * (2 * WS - 1) + j % WS)]);
                   pv[e] = fast_exp2(sc - mrow);
+                  ls[((i >> 1) & 1) * 2 + e] += pv[e];   // four independent partial sums
                 } else {
                   pv[e] = 0.0f;
                 }
-                lsum += pv[e];
               }
               pk[i >> 1] = pack_bf16(pv[0], pv[1]);
             }
@@ -371,7 +382,41 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
                            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                            : "memory");
             }
+          };
+          if (Cfg::NCH == 2) {
+            // the whole row fits in registers: one trip to TMEM serves the maximum and the exponentials
+            tmem_ld32_nowait(srow, r[0]);
+            tmem_ld32_nowait(srow + 32, r[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (i < N) mx = fmaxf(mx, __uint_as_float(r[i >> 5][i & 31]));
+            // upper bound of the maximum of (scaled score + bias): softmax is exact after normalisation, no overflow
+            mrow = fmaf(mx, scale_log2e, tabmax);
+            emit(0, r[0]);
+            emit(1, r[1]);
+          } else {
+            // two passes over the row, the TMEM load of chunk c + 1 in flight while chunk c is worked on
+            tmem_ld32_nowait(srow, r[0]);
+#pragma unroll
+            for (int c = 0; c < Cfg::NCH; ++c) {
+              tmem_ld_wait();
+              if (c + 1 < Cfg::NCH) tmem_ld32_nowait(srow + (c + 1) * 32, r[(c + 1) & 1]);
+              else tmem_ld32_nowait(srow, r[(c + 1) & 1]);   // first chunk of the second pass
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(r[c & 1][i]));
+            }
+            mrow = fmaf(mx, scale_log2e, tabmax);
+            constexpr int B0 = Cfg::NCH & 1;   // buffer that holds chunk 0 of the second pass
+#pragma unroll
+            for (int c = 0; c < Cfg::NCH; ++c) {
+              tmem_ld_wait();
+              if (c + 1 < Cfg::NCH) tmem_ld32_nowait(srow + (c + 1) * 32, r[(B0 + c + 1) & 1]);
+              emit(c, r[(B0 + c) & 1]);
+            }
           }
+          lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
           tmem_st_wait();
         }
         tc_fence_before();
@@ -465,6 +510,18 @@ int launch_ws(const bf16* qkv, const bf16* qg, const float* table, bf16* out, in
                                           1.4426950408889634f / sqrtf((float)HD));
   VIP_CUDA(cudaGetLastError());
   count_launch();
+#ifdef VIP_ATTN_TRACE
+  {
+    long long t[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(t, g_attn_trace, sizeof(t));
+    if (t[0] > 0)
+      fprintf(stderr, "[attn trace ws%d] jobs %lld  QK->S %lld  S->P %lld  P->O %lld cycles/job\n", WS, t[0], t[1] / t[0],
+              t[2] / t[0], t[3] / t[0]);
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_attn_trace, z, sizeof(z));
+  }
+#endif
   return VIP_OK;
 }
 
