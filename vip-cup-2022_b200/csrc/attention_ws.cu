@@ -153,6 +153,9 @@ struct WsCfg {
   static constexpr int S_COL = 0;
   static constexpr int P_COL = WS <= 8 ? 128 : 0;         // ws 14: P overwrites the columns of S already consumed
   static constexpr int O_COL = WS <= 8 ? 192 : 208;
+  // P reaches the MMA issuer in parts (ws 14: after chunks 1, 3, 5 and 6 = K steps 0-3, 4-7, 8-11, 12), so that most of
+  // P V runs underneath the exponentials of the later chunks
+  static constexpr int NPART = WS <= 8 ? 1 : 4;
   static constexpr int kThreads = 11 * 32;
   static_assert(kStageBytes % 1024 == 0 && O_COL + 32 <= 256, "layout");
   static int smem_bytes(int heads) {
@@ -178,10 +181,10 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint64_t* full = bars;                 // [kStages] TMA -> MMA warps
   uint64_t* empty = full + kStages;      // [kStages] both MMA warps -> producer
   uint64_t* s_full = empty + kStages;    // [2] S of group g is in TMEM
-  uint64_t* p_full = s_full + 2;         // [2] group g has written P (and is done with S)
-  uint64_t* o_full = p_full + 2;         // [2] O of group g is in TMEM
+  uint64_t* p_full = s_full + 2;         // [2][4] group g has written part k of P (the last part: and is done with S)
+  uint64_t* o_full = p_full + 8;         // [2] O of group g is in TMEM
   uint64_t* o_free = o_full + 2;         // [2] group g has read O
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);  // (barrier block: 2 * kStages + 16 words)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWw = W / WS, nWimg = (H / WS) * nWw;
@@ -197,7 +200,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full + g, 1);
-      mbar_init(p_full + g, 128);
+      for (int k = 0; k < 4; ++k) mbar_init(p_full + g * 4 + k, 128);
       mbar_init(o_full + g, 1);
       mbar_init(o_free + g, 128);
     }
@@ -288,15 +291,19 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           mbar_wait(s_full + g, job & 1u);
           const long long t1 = clock64();
 #endif
-          mbar_wait(p_full + g, job & 1u);
+          mbar_wait(o_free + g, (job & 1u) ^ 1u);   // O of the previous job has been read
+#pragma unroll
+          for (int part = 0; part < Cfg::NPART; ++part) {
+            mbar_wait(p_full + g * 4 + part, job & 1u);
+            tc_fence_after();
+            constexpr int SPP = Cfg::NPART == 1 ? Cfg::KSTEPS : 4;   // K steps per part
+#pragma unroll
+            for (int k = part * SPP; k < (part + 1) * SPP && k < Cfg::KSTEPS; ++k)
+              umma_ts(tg + Cfg::O_COL, tg + Cfg::P_COL + 8 * k, vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
+          }
 #ifdef VIP_ATTN_TRACE
           const long long t2 = clock64();
 #endif
-          mbar_wait(o_free + g, (job & 1u) ^ 1u);   // O of the previous job has been read
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < Cfg::KSTEPS; ++k)
-            umma_ts(tg + Cfg::O_COL, tg + Cfg::P_COL + 8 * k, vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
           umma_commit(o_full + g);
           if (mt == MT - 1) umma_commit(empty + s);
 #ifdef VIP_ATTN_TRACE
@@ -374,6 +381,12 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
               }
               pk[i >> 1] = pack_bf16(pv[0], pv[1]);
             }
+            if (Cfg::NPART > 1 && c > 0 && (c & 1) == 0) {
+              // the stores of the chunks before this one have long landed: hand that part of P to the MMA issuer
+              tmem_st_wait();
+              tc_fence_before();
+              mbar_arrive(p_full + g * 4 + (c >> 1) - 1);
+            }
             // only the columns that exist in P (ws 14: 104, the last chunk is half a chunk)
             if (c * 32 + 32 <= KEYS || WPT == 2) {
               tmem_st16(prow + c * 16, pk);
@@ -418,9 +431,12 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           }
           lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
           tmem_st_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k + 1 < Cfg::NPART; ++k) mbar_arrive(p_full + g * 4 + k);
         }
         tc_fence_before();
-        mbar_arrive(p_full + g);
+        mbar_arrive(p_full + g * 4 + Cfg::NPART - 1);
         // ---- O / row sum -> bf16 -> global
         mbar_wait(o_full + g, job & 1u);
         tc_fence_after();
