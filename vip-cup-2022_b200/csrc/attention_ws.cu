@@ -134,6 +134,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ long long g_attn_trace[8];
 #endif
 
+// packed fp32 pairs (FFMA2 / FADD2 of sm_100): half the issue slots of the softmax arithmetic
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmov.b64 rc, {%6,%7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nadd.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 template <int WS>
 struct WsCfg {
   static constexpr int N = WS * WS;                       // tokens of a window (49 / 196)
@@ -361,25 +378,28 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           const uint32_t prow = tl + Cfg::P_COL + jq * (WKEYS / 2);
           uint32_t r[2][32];
           float mx = -3.0e38f, mrow;
-          float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          float2 ls[2] = {make_float2(0.0f, 0.0f), make_float2(0.0f, 0.0f)};
           // P chunk c = exp2(score * scale + bias - mrow) of the 32 raw scores in `rc`, packed bf16 pairs back into TMEM
           auto emit = [&](const int c, const uint32_t (&rc)[32]) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              float pv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int j = c * 32 + i + e;          // key = (j / WS, j % WS), compile-time after unrolling
-                if (j < N) {
-                  const float sc = fmaf(__uint_as_float(rc[i + e]), scale_log2e, pb[-((j / WS) * (2 * WS - 1) + j % WS)]);
-                  pv[e] = fast_exp2(sc - mrow);
-                  ls[((i >> 1) & 1) * 2 + e] += pv[e];   // four independent partial sums
-                } else {
-                  pv[e] = 0.0f;
-                }
+              const int j = c * 32 + i;              // keys j, j + 1 = (j / WS, j % WS), compile-time after unrolling
+              float2 pv = make_float2(0.0f, 0.0f);
+              if (j + 1 < N) {
+                const float2 bias = make_float2(pb[-((j / WS) * (2 * WS - 1) + j % WS)],
+                                                pb[-(((j + 1) / WS) * (2 * WS - 1) + (j + 1) % WS)]);
+                float2 sc = ffma2(make_float2(__uint_as_float(rc[i]), __uint_as_float(rc[i + 1])),
+                                  make_float2(scale_log2e, scale_log2e), bias);
+                sc = fadd2(sc, make_float2(-mrow, -mrow));
+                pv = make_float2(fast_exp2(sc.x), fast_exp2(sc.y));
+                ls[(i >> 1) & 1] = fadd2(ls[(i >> 1) & 1], pv);   // four independent partial sums
+              } else if (j < N) {
+                const float sc = fmaf(__uint_as_float(rc[i]), scale_log2e, pb[-((j / WS) * (2 * WS - 1) + j % WS)]);
+                pv.x = fast_exp2(sc - mrow);
+                ls[0].x += pv.x;
               }
-              pk[i >> 1] = pack_bf16(pv[0], pv[1]);
+              pk[i >> 1] = pack_bf16(pv.x, pv.y);
             }
             if (Cfg::NPART > 1 && c > 0 && (c & 1) == 0) {
               // the stores of the chunks before this one have long landed: hand that part of P to the MMA issuer
@@ -429,7 +449,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
               emit(c, r[(B0 + c) & 1]);
             }
           }
-          lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          lsum = (ls[0].x + ls[0].y) + (ls[1].x + ls[1].y);
           tmem_st_wait();
         } else {
 #pragma unroll
@@ -448,6 +468,8 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         tc_fence_before();
         mbar_arrive(o_free + g);
         if (row_ok) {
+          // 64 contiguous bytes per thread (two full sectors).  Staging the rows through shared memory for wider
+          // coalescing was measured slower: the address arithmetic per staged row costs more than the stores save.
           const float inv = 1.0f / lsum;
           const long long grow = ((long long)b * H + wy * WS + tok / WS) * W + wx * WS + tok % WS;
           uint4* op = reinterpret_cast<uint4*>(out + grow * C + h * HD);
