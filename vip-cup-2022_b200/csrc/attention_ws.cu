@@ -23,6 +23,10 @@
 
 #include "common.cuh"
 
+#ifndef VIP_ATTN_POLY
+#define VIP_ATTN_POLY 1   // measured on B200 (ws 14, batch 1024): 0 -> 218 us, 1 -> 192, 2 -> 199, 3 -> 220
+#endif
+
 namespace vip {
 namespace {
 
@@ -151,6 +155,24 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// exp2 of a pair of non-positive arguments on the FMA / ALU pipes (no MUFU): x = n + f with n = round(x), 2^f by a
+// degree-3 polynomial on [-0.5, 0.5] (max relative error 7.5e-5, well under the bf16 rounding of P), 2^n by adding n to
+// the exponent field.  The softmax is bound by MUFU.EX2 issue (one warp instruction per 8 cycles and scheduler), so a
+// share of the exponentials is moved here.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: the low mantissa bits of x + magic hold n
+  const float2 t = fadd2(x, magic);
+  const float2 nf = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = fadd2(x, make_float2(-nf.x, -nf.y));
+  float2 p = ffma2(make_float2(0.05517144873738289f, 0.05517144873738289f), f, make_float2(0.2426108419895172f, 0.2426108419895172f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 template <int WS>
 struct WsCfg {
   static constexpr int N = WS * WS;                       // tokens of a window (49 / 196)
@@ -173,6 +195,7 @@ struct WsCfg {
   // P reaches the MMA issuer in parts (ws 14: after chunks 1, 3, 5 and 6 = K steps 0-3, 4-7, 8-11, 12), so that most of
   // P V runs underneath the exponentials of the later chunks
   static constexpr int NPART = WS <= 8 ? 1 : 4;
+  static constexpr int kPolyOf4 = VIP_ATTN_POLY;          // of every 4 pairs of exponentials, how many avoid the MUFU pipe
   static constexpr int kThreads = 11 * 32;
   static_assert(kStageBytes % 1024 == 0 && O_COL + 32 <= 256, "layout");
   static int smem_bytes(int heads) {
@@ -392,7 +415,8 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
                 float2 sc = ffma2(make_float2(__uint_as_float(rc[i]), __uint_as_float(rc[i + 1])),
                                   make_float2(scale_log2e, scale_log2e), bias);
                 sc = fadd2(sc, make_float2(-mrow, -mrow));
-                pv = make_float2(fast_exp2(sc.x), fast_exp2(sc.y));
+                if (((i >> 1) & 3) < Cfg::kPolyOf4) pv = exp2_poly2(sc);
+                else pv = make_float2(fast_exp2(sc.x), fast_exp2(sc.y));
                 ls[(i >> 1) & 1] = fadd2(ls[(i >> 1) & 1], pv);   // four independent partial sums
               } else if (j < N) {
                 const float sc = fmaf(__uint_as_float(rc[i]), scale_log2e, pb[-((j / WS) * (2 * WS - 1) + j % WS)]);
