@@ -191,13 +191,13 @@ struct WsCfg {
   // TMEM columns of one softmax group
   static constexpr int S_COL = 0;
   static constexpr int P_COL = WS <= 8 ? 128 : 0;         // ws 14: P overwrites the columns of S already consumed
-  static constexpr int O_COL = WS <= 8 ? 192 : 208;
+  static constexpr int O_COL = WS <= 8 ? 192 : 208;       // ws 7: two O buffers (192, 224), read out one job late
   // P reaches the MMA issuer in parts (ws 14: after chunks 1, 3, 5 and 6 = K steps 0-3, 4-7, 8-11, 12), so that most of
   // P V runs underneath the exponentials of the later chunks
   static constexpr int NPART = WS <= 8 ? 1 : 4;
   static constexpr int kPolyOf4 = VIP_ATTN_POLY;          // of every 4 pairs of exponentials, how many avoid the MUFU pipe
   static constexpr int kThreads = 11 * 32;
-  static_assert(kStageBytes % 1024 == 0 && O_COL + 32 <= 256, "layout");
+  static_assert(kStageBytes % 1024 == 0 && O_COL + (WS <= 8 ? 64 : 32) <= 256, "layout");
   static int smem_bytes(int heads) {
     return 1024 + kStages * kStageBytes + ((heads * TAB * 4 + 15) / 16) * 16 + ((heads * 4 + 15) / 16) * 16 + 256;
   }
@@ -222,9 +222,10 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint64_t* empty = full + kStages;      // [kStages] both MMA warps -> producer
   uint64_t* s_full = empty + kStages;    // [2] S of group g is in TMEM
   uint64_t* p_full = s_full + 2;         // [2][4] group g has written part k of P (the last part: and is done with S)
-  uint64_t* o_full = p_full + 8;         // [2] O of group g is in TMEM
-  uint64_t* o_free = o_full + 2;         // [2] group g has read O
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);  // (barrier block: 2 * kStages + 16 words)
+  uint64_t* o_full = p_full + 8;         // [2][2] O buffer b of group g is in TMEM (ws 14 uses buffer 0 only)
+  uint64_t* o_free = o_full + 4;         // [2][2] group g has read O buffer b
+  uint64_t* s_free = o_free + 4;         // [2] group g holds its S row in registers (ws 7): the next Q K^T may overwrite S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);  // (barrier block: 2 * kStages + 22 words)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWw = W / WS, nWimg = (H / WS) * nWw;
@@ -241,8 +242,11 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full + g, 1);
       for (int k = 0; k < 4; ++k) mbar_init(p_full + g * 4 + k, 128);
-      mbar_init(o_full + g, 1);
-      mbar_init(o_free + g, 128);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(o_full + g * 2 + b, 1);
+        mbar_init(o_free + g * 2 + b, 128);
+      }
+      mbar_init(s_free + g, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -305,6 +309,49 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       const uint32_t tg = tmem_base + (uint32_t)(g * 256);
       int n = 0;
       uint32_t job = 0;
+      if constexpr (WS <= 8) {
+        // ws 7: the group copies its 49 scores into registers at once and releases S, so Q K^T of job j + 1 is issued
+        // BEFORE P V of job j and runs underneath the softmax of job j; O alternates between two TMEM buffers and is
+        // read out one job late.  Neither MMA round trip is on the group's critical path any more.
+        bool have_prev = false;
+        int prev_s = 0;
+        uint64_t prev_vdesc = 0;
+        auto issue_pv = [&](uint32_t j) {      // P V of job j into O buffer j & 1
+          const uint32_t b = j & 1u, u = j >> 1;
+          mbar_wait(p_full + g * 4, j & 1u);
+          mbar_wait(o_free + g * 2 + b, (u & 1u) ^ 1u);   // the previous use of this buffer has been read out
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < Cfg::KSTEPS; ++k)
+            umma_ts(tg + Cfg::O_COL + 32 * b, tg + Cfg::P_COL + 8 * k, prev_vdesc + (uint64_t)(k * 128), idesc_o, k > 0 ? 1u : 0u);
+          umma_commit(o_full + g * 2 + b);
+          umma_commit(empty + prev_s);
+        };
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+          const int s = n % kStages;
+          const uint32_t ph = (uint32_t)(n / kStages) & 1u;
+          const int tile = item / num_hp, hp = item - tile * num_hp;
+          mbar_wait(full + s, ph);
+          if (hp * 2 + g >= heads) {
+            mbar_arrive(empty + s);
+            continue;
+          }
+          mbar_wait(s_free + g, (job & 1u) ^ 1u);         // S of the previous job is in the group's registers
+          tc_fence_after();
+          const uint32_t sQ = smem_u32(stage0 + s * Cfg::kStageBytes);
+          const uint32_t sK = sQ + Cfg::kQBytes, sV = sK + Cfg::kKBytes;
+          const uint64_t qdesc = make_sw128_desc(sQ) + 4 * g, kdesc = make_sw128_desc(sK) + 4 * g;
+          umma_ss(tg + Cfg::S_COL, qdesc, kdesc, idesc_s, 0u);
+          umma_ss(tg + Cfg::S_COL, qdesc + 2, kdesc + 2, idesc_s, 1u);
+          umma_commit(s_full + g);
+          if (have_prev) issue_pv(job - 1u);
+          have_prev = true;
+          prev_s = s;
+          prev_vdesc = make_sw128_desc(sV) + 4 * g;
+          ++job;
+        }
+        if (have_prev) issue_pv(job - 1u);
+      } else
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
         const int s = n % kStages;
         const uint32_t ph = (uint32_t)(n / kStages) & 1u;
@@ -331,7 +378,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           mbar_wait(s_full + g, job & 1u);
           const long long t1 = clock64();
 #endif
-          mbar_wait(o_free + g, (job & 1u) ^ 1u);   // O of the previous job has been read
+          mbar_wait(o_free + g * 2, (job & 1u) ^ 1u);   // O of the previous job has been read
 #pragma unroll
           for (int part = 0; part < Cfg::NPART; ++part) {
             mbar_wait(p_full + g * 4 + part, job & 1u);
@@ -344,10 +391,10 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #ifdef VIP_ATTN_TRACE
           const long long t2 = clock64();
 #endif
-          umma_commit(o_full + g);
+          umma_commit(o_full + g * 2);
           if (mt == MT - 1) umma_commit(empty + s);
 #ifdef VIP_ATTN_TRACE
-          mbar_wait(o_full + g, job & 1u);
+          mbar_wait(o_full + g * 2, job & 1u);
           const long long t3 = clock64();
           if (blockIdx.x == 0 && g == 0) {
             g_attn_trace[0] += 1;
@@ -374,6 +421,33 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       tmem_st_wait();
     }
     uint32_t job = 0;
+    // ws 7: O is read out one job late from one of two TMEM buffers (see the MMA issuer)
+    bool pend = false;
+    float pend_inv = 0.0f;
+    uint4* pend_dst = nullptr;               // null: the row does not exist
+    auto wait_prev_pv = [&]() {              // P V of job - 1 has completed: P may be overwritten, O buffer is valid
+      const uint32_t j = job - 1u;
+      mbar_wait(o_full + g * 2 + (j & 1u), (j >> 1) & 1u);
+      tc_fence_after();
+    };
+    auto read_out_prev = [&]() {             // O of job - 1 -> registers -> / row sum -> bf16 -> global
+      const uint32_t j = job - 1u;
+      uint32_t ro[32];
+      tmem_ld32_nowait(tl + Cfg::O_COL + 32 * (j & 1u), ro);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free + g * 2 + (j & 1u));
+      if (pend_dst != nullptr) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            w[t] = pack_bf16(__uint_as_float(ro[q4 * 8 + 2 * t]) * pend_inv, __uint_as_float(ro[q4 * 8 + 2 * t + 1]) * pend_inv);
+          pend_dst[q4] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    };
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int tile = item / num_hp, hp = item - tile * num_hp;
       const int h = hp * 2 + g;
@@ -445,11 +519,14 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
             tmem_ld32_nowait(srow, r[0]);
             tmem_ld32_nowait(srow + 32, r[1]);
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free + g);           // the next Q K^T may overwrite S
 #pragma unroll
             for (int i = 0; i < 64; ++i)
               if (i < N) mx = fmaxf(mx, __uint_as_float(r[i >> 5][i & 31]));
             // upper bound of the maximum of (scaled score + bias): softmax is exact after normalisation, no overflow
             mrow = fmaf(mx, scale_log2e, tabmax);
+            if (pend) wait_prev_pv();          // (long done) before P is overwritten
             emit(0, r[0]);
             emit(1, r[1]);
           } else {
@@ -481,8 +558,16 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         }
         tc_fence_before();
         mbar_arrive(p_full + g * 4 + Cfg::NPART - 1);
+        if constexpr (WS <= 8) {
+          if (pend) read_out_prev();
+          pend = true;
+          pend_inv = 1.0f / lsum;
+          pend_dst = row_ok ? reinterpret_cast<uint4*>(out + (((long long)b * H + wy * WS + tok / WS) * W + wx * WS + tok % WS) * C + h * HD)
+                            : nullptr;
+          continue;
+        }
         // ---- O / row sum -> bf16 -> global
-        mbar_wait(o_full + g, job & 1u);
+        mbar_wait(o_full + g * 2, job & 1u);
         tc_fence_after();
         uint32_t r[32];
         if (warp_live) {
@@ -490,7 +575,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(o_free + g);
+        mbar_arrive(o_free + g * 2);
         if (row_ok) {
           // 64 contiguous bytes per thread (two full sectors).  Staging the rows through shared memory for wider
           // coalescing was measured slower: the address arithmetic per staged row costs more than the stores save.
@@ -507,6 +592,10 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
           }
         }
       }
+    }
+    if (pend) {   // ws 7: drain the last job
+      wait_prev_pv();
+      read_out_prev();
     }
   }
   tc_fence_before();
