@@ -127,3 +127,27 @@ def test_dwconv_fused_squeeze(cuda_device):
     torch.cuda.synchronize()
     assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
     assert torch.allclose(gap, y.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("m,c", [(1000, 64), (4099, 96), (777, 128), (513, 192), (300, 384), (65, 768)])
+def test_layernorm_matches_torch(cuda_device, m, c):
+    """vip_layernorm_bf16 (block.py:28,39; feature.py:100-101; gcvit.py:79): thread-per-row kernel for C <= 128, lane-group
+    kernel above, against fp32 torch on the same bf16 input; row_stats = (sum, sum of squares) of the ROUNDED output rows.
+    Tolerance: one bf16 ulp of the output (2^-8 relative) + 1e-3."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(m + c)
+    x = (torch.randn((m, c), generator=g) * 2.0 + 0.5).to(torch.bfloat16).to(cuda_device)
+    gamma = (torch.rand((c,), generator=g) + 0.5).to(cuda_device)
+    beta = (torch.randn((c,), generator=g) * 0.3).to(cuda_device)
+    stats = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
+    got = nn.layernorm(x, gamma, beta, eps=1e-5, row_stats=stats)
+    ref = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    err = (got.float() - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 1e-3).all(), err.max().item()
+    gf = got.float()
+    assert torch.allclose(stats[:, 0], gf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (gf * gf).sum(1), rtol=1e-4, atol=1e-2)
