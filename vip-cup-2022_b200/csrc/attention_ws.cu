@@ -234,6 +234,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   const int total_items = num_tiles * num_hp;
   const int ldq = (global_q ? 2 : 3) * C;
 
+  pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(full + i, 1);
@@ -270,6 +271,7 @@ window_attention_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   }
   __syncthreads();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // set-up (barriers, TMEM, zeroed stages, bias tables = weights) overlapped the preceding kernel's tail
 
   if (warp == 8) {
     // ---------------- producer ----------------
@@ -657,8 +659,8 @@ int launch_ws(const bf16* qkv, const bf16* qg, const float* table, bf16* out, in
   const int num_windows = B * (H / WS) * (W / WS);
   const int items = ((num_windows + Cfg::WPT - 1) / Cfg::WPT) * ((heads + 1) / 2);
   const int grid = items < sms ? items : sms;
-  kern<<<grid, Cfg::kThreads, smem, st>>>(tmQKV, tmQG, table, out, H, W, C, heads, num_windows, qg ? 1 : 0,
-                                          1.4426950408889634f / sqrtf((float)HD));
+  VIP_LAUNCH(kern, grid, Cfg::kThreads, smem, st, tmQKV, tmQG, table, out, H, W, C, heads, num_windows, qg ? 1 : 0,
+             1.4426950408889634f / sqrtf((float)HD));
   VIP_CUDA(cudaGetLastError());
   count_launch();
 #ifdef VIP_ATTN_TRACE

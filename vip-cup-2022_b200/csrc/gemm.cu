@@ -443,6 +443,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int total_tiles = g.m_tiles * g.n_tiles;
   const GemmEpilogue& e = g.epi;
   const bool has_res = e.residual != nullptr;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -482,6 +483,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (kPair) cluster_sync_all();   // both CTAs' barriers are initialised before anything arrives on them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (descriptor prefetch, barriers, TMEM) overlapped the tail of the preceding kernel; from here on the
+  // kernel reads and writes activations
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -912,7 +916,7 @@ int num_sms() {
 int ensure_neutral(cudaStream_t st) {
   static bool done = false;  // per process (one device per process in this library's use)
   if (!done) {
-    init_neutral_kernel<<<8, 256, 0, st>>>();
+    init_neutral_kernel<<<8, 256, 0, st>>>();   // (once per process, plain launch)
     VIP_CUDA(cudaGetLastError());
     done = true;
   }
@@ -940,16 +944,18 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     cfg.blockDim = dim3(C::kThreads);
     cfg.dynamicSmemBytes = C::kSmem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     VIP_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, g));
   } else {
-    kern<<<grid, C::kThreads, C::kSmem, st>>>(tmA, tmB, tmC, tmR, g);
+    VIP_LAUNCH(kern, grid, C::kThreads, C::kSmem, st, tmA, tmB, tmC, tmR, g);
   }
   VIP_CUDA(cudaGetLastError());
   count_launch();

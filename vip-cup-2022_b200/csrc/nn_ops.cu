@@ -49,6 +49,8 @@ inline int grid_for(long long work, int block) {
 // feature.py:98).  K order = (r, s, c), matching Keras kernels (kh, kw, Cin, Cout) flattened over the first 3 axes.
 __global__ void im2col_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int ks,
                                    int stride, int pad, int Ho, int Wo, int Kp) {
+  pdl_trigger();
+  pdl_wait();
   const int c8n = C >> 3;
   const long long per_row = (long long)ks * ks * c8n;
   const long long total = (long long)N * Ho * Wo * per_row;
@@ -72,6 +74,8 @@ __global__ void im2col_vec8_kernel(const bf16* __restrict__ x, bf16* __restrict_
 template <int KP, int KS, int CI>
 __global__ void im2col_row_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int stride,
                                   int pad, int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
   static_assert(KS * KS * CI <= KP && KP % 8 == 0, "row does not fit");
   const long long total = (long long)N * Ho * Wo;
   for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
@@ -108,6 +112,8 @@ __global__ void im2col_row_kernel(const bf16* __restrict__ x, bf16* __restrict__
 }
 __global__ void im2col_scalar_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int ks,
                                      int stride, int pad, int Ho, int Wo, int Kp) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * Ho * Wo * Kp;
   const int K = ks * ks * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -130,6 +136,8 @@ __global__ void im2col_scalar_kernel(const bf16* __restrict__ x, bf16* __restric
 // ---- AveragePooling2D(2, 2, 'same') (resnet_rs_model.py:207-212): divisor = number of valid inputs
 __global__ void avgpool2_same_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int Ho,
                                      int Wo) {
+  pdl_trigger();
+  pdl_wait();
   const int c8n = C >> 3;
   const long long total = (long long)N * Ho * Wo * c8n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -163,6 +171,8 @@ __global__ void avgpool2_same_kernel(const bf16* __restrict__ x, bf16* __restric
 // ---- GlobalAveragePooling2D over [N, HW, C] -> [N, C] (bf16 and/or f32 out).  Block = (image, 64-channel slab).
 __global__ void __launch_bounds__(256) global_avgpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ out_bf16,
                                                              float* __restrict__ out_f32, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32][65];
   const int n = blockIdx.x, c0 = blockIdx.y * 64;
   const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;  // 8 channel-octets x 32 row lanes
@@ -194,6 +204,8 @@ __global__ void __launch_bounds__(256) global_avgpool_kernel(const bf16* __restr
 __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __restrict__ gate,
                                      const bf16* __restrict__ shortcut, bf16* __restrict__ out, long long total8, int HW,
                                      int C, int act) {
+  pdl_trigger();
+  pdl_wait();
   const int c8n = C >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % c8n);
@@ -228,6 +240,8 @@ template <int NC8>
 __global__ void __launch_bounds__(128) layernorm_row_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ out,
                                                             float* __restrict__ row_stats, long long M, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = NC8 * 8;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
@@ -291,6 +305,8 @@ template <int LPR, int J, int U>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
                                                         float* __restrict__ row_stats, long long M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;  // rows per warp and group
   const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -430,6 +446,8 @@ template <int P, int D, int MINB>  // channel pairs per thread: 4 (16-byte acces
 __global__ void __launch_bounds__(128, MINB) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[3][3][C]*/,
                                                         bf16* __restrict__ out, float* __restrict__ gap /*[N][C] or null*/,
                                                         int N, int H, int W, int C, int gelu) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = 2 * P, BYTES = 4 * P, RING = D + 1;
   __shared__ __align__(16) uint8_t ring[RING * 3 * 128 * BYTES];
   const int cvn = C / V;
@@ -536,6 +554,8 @@ __global__ void __launch_bounds__(128, MINB) dwconv3x3_kernel(const bf16* __rest
 // ---- ZeroPadding2D(1) + MaxPool2D(3, 2, 'valid') (feature.py:139,151-152): the padded zeros take part in the max
 __global__ void maxpool3s2_zeropad_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C,
                                           int Ho, int Wo) {
+  pdl_trigger();
+  pdl_wait();
   const int c8n = C >> 3;
   const long long total = (long long)N * Ho * Wo * c8n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -572,6 +592,8 @@ __global__ void maxpool3s2_zeropad_kernel(const bf16* __restrict__ x, bf16* __re
 __global__ void head_kernel(const float* __restrict__ feat, const float* __restrict__ w /*[C][k]*/,
                             const float* __restrict__ b, float* __restrict__ probs, double* __restrict__ acc,
                             double acc_weight, int N, int C, int k, int sigmoid_head) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   float z[8];
@@ -608,12 +630,16 @@ __global__ void head_kernel(const float* __restrict__ feat, const float* __restr
 
 // ---- f32 -> bf16 cast (network input when the preprocessing output is kept in fp32)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(x[i]);
 }
 
 // ---- out = bf16(x * scale): pooled sums -> means as a GEMM operand (SE squeeze, resnet_rs_model.py:149)
 __global__ void scale_cast_f32_bf16_kernel(const float* __restrict__ x, float scale, bf16* __restrict__ out, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(x[i] * scale);
 }
@@ -638,15 +664,12 @@ extern "C" int vip_im2col_bf16(const void* x, int N, int H, int W, int C, int ks
   const bool vec = (C % 8 == 0) && Kp == ksize * ksize * C;
   if (vec) {
     const long long work = (long long)N * Ho * Wo * ksize * ksize * (C / 8);
-    im2col_vec8_kernel<<<grid_for(work, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N, H, W, C, ksize, stride,
-                                                                    pad, Ho, Wo, Kp);
+    VIP_LAUNCH((im2col_vec8_kernel), grid_for(work, 256), 256, 0, ST(stream), (const bf16*)x, (bf16*)out, N, H, W, C, ksize, stride, pad, Ho, Wo, Kp);
   } else if (Kp == 32 && ksize == 3 && C == 3) {
-    im2col_row_kernel<32, 3, 3><<<grid_for((long long)N * Ho * Wo, 128), 128, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N,
-                                                                                             H, W, stride, pad, Ho, Wo);
+    VIP_LAUNCH((im2col_row_kernel<32, 3, 3>), grid_for((long long)N * Ho * Wo, 128), 128, 0, ST(stream), (const bf16*)x, (bf16*)out, N, H, W, stride, pad, Ho, Wo);
   } else {
     const long long work = (long long)N * Ho * Wo * Kp;
-    im2col_scalar_kernel<<<grid_for(work, 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out, N, H, W, C, ksize,
-                                                                      stride, pad, Ho, Wo, Kp);
+    VIP_LAUNCH((im2col_scalar_kernel), grid_for(work, 256), 256, 0, ST(stream), (const bf16*)x, (bf16*)out, N, H, W, C, ksize, stride, pad, Ho, Wo, Kp);
   }
   LAUNCH_CHECK();
 }
@@ -654,15 +677,14 @@ extern "C" int vip_im2col_bf16(const void* x, int N, int H, int W, int C, int ks
 extern "C" int vip_avgpool2_same_bf16(const void* x, int N, int H, int W, int C, void* out, void* stream) {
   VIP_REQUIRE(x && out && C % 8 == 0, VIP_ERR_INVALID, "vip_avgpool2_same_bf16: bad argument (C %% 8)");
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  avgpool2_same_kernel<<<grid_for((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out,
-                                                                                               N, H, W, C, Ho, Wo);
+  VIP_LAUNCH((avgpool2_same_kernel), grid_for((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream), (const bf16*)x, (bf16*)out, N, H, W, C, Ho, Wo);
   LAUNCH_CHECK();
 }
 
 extern "C" int vip_global_avgpool_bf16(const void* x, int N, int HW, int C, void* out_bf16, float* out_f32, void* stream) {
   VIP_REQUIRE(x && (out_bf16 || out_f32) && C % 8 == 0, VIP_ERR_INVALID, "vip_global_avgpool_bf16: bad argument");
   dim3 grid(N, (C + 63) / 64);
-  global_avgpool_kernel<<<grid, 256, 0, ST(stream)>>>((const bf16*)x, (bf16*)out_bf16, out_f32, HW, C);
+  VIP_LAUNCH((global_avgpool_kernel), grid, 256, 0, ST(stream), (const bf16*)x, (bf16*)out_bf16, out_f32, HW, C);
   LAUNCH_CHECK();
 }
 
@@ -670,8 +692,7 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
                                       int C, int act, void* stream) {
   VIP_REQUIRE(y && out && C % 8 == 0, VIP_ERR_INVALID, "vip_scale_add_act_bf16: bad argument");
   const long long total8 = (long long)N * HW * (C / 8);
-  scale_add_act_kernel<<<grid_for(total8, 256), 256, 0, ST(stream)>>>((const bf16*)y, gate, (const bf16*)shortcut,
-                                                                      (bf16*)out, total8, HW, C, act);
+  VIP_LAUNCH((scale_add_act_kernel), grid_for(total8, 256), 256, 0, ST(stream), (const bf16*)y, gate, (const bf16*)shortcut, (bf16*)out, total8, HW, C, act);
   LAUNCH_CHECK();
 }
 
@@ -684,14 +705,14 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
   const int c8n = C / 8;
   cudaStream_t st = ST(stream);
   const unsigned rgrid = (unsigned)((M + 127) / 128);
-  if (c8n == 8) layernorm_row_kernel<8><<<rgrid, 128, 0, st>>>(xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n == 12) layernorm_row_kernel<12><<<rgrid, 128, 0, st>>>(xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n == 16) layernorm_row_kernel<16><<<rgrid, 128, 0, st>>>(xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n <= 8) layernorm_kernel<8, 1, 1><<<grid_for(M * 8, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 16) layernorm_kernel<16, 1, 1><<<grid_for(M * 16, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 32) layernorm_kernel<32, 1, 1><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 64) layernorm_kernel<32, 2, 1><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
-  else layernorm_kernel<32, 4, 1><<<grid_for(M * 32, 256), 256, 0, st>>>(xp, gamma, beta, op, row_stats, M, C, eps);
+  if (c8n == 8) VIP_LAUNCH((layernorm_row_kernel<8>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
+  else if (c8n == 12) VIP_LAUNCH((layernorm_row_kernel<12>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
+  else if (c8n == 16) VIP_LAUNCH((layernorm_row_kernel<16>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
+  else if (c8n <= 8) VIP_LAUNCH((layernorm_kernel<8, 1, 1>), grid_for(M * 8, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 16) VIP_LAUNCH((layernorm_kernel<16, 1, 1>), grid_for(M * 16, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 32) VIP_LAUNCH((layernorm_kernel<32, 1, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 64) VIP_LAUNCH((layernorm_kernel<32, 2, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else VIP_LAUNCH((layernorm_kernel<32, 4, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
   LAUNCH_CHECK();
 }
 
@@ -701,34 +722,32 @@ extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, floa
   // measured at [1024, 100, 100, 96] on B200: 8 channels per thread, 4 rows ahead, 3 blocks per SM (168 registers) 1.59 ms;
   // 2 blocks (202 registers) 1.61; depth 2 / 6 the same; 4 channels per thread 1.73; the register-window version 2.21
   const long long threads = (long long)N * W * (C / 8);
-  dwconv3x3_kernel<4, 4, 3><<<(unsigned)((threads + 127) / 128), 128, 0, ST(stream)>>>((const bf16*)x, w, (bf16*)out, gap, N,
-                                                                                          H, W, C, gelu);
+  VIP_LAUNCH((dwconv3x3_kernel<4, 4, 3>), (unsigned)((threads + 127) / 128), 128, 0, ST(stream), (const bf16*)x, w, (bf16*)out, gap, N, H, W, C, gelu);
   LAUNCH_CHECK();
 }
 
 extern "C" int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* stream) {
   VIP_REQUIRE(x && out && C % 8 == 0, VIP_ERR_INVALID, "vip_maxpool3s2_bf16: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool3s2_zeropad_kernel<<<grid_for((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream)>>>(
-      (const bf16*)x, (bf16*)out, N, H, W, C, Ho, Wo);
+  VIP_LAUNCH((maxpool3s2_zeropad_kernel), grid_for((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream), (const bf16*)x, (bf16*)out, N, H, W, C, Ho, Wo);
   LAUNCH_CHECK();
 }
 
 extern "C" int vip_head_f32(const float* feat, const float* w, const float* b, float* probs, double* acc,
                             double acc_weight, int N, int C, int k, int sigmoid_head, void* stream) {
   VIP_REQUIRE(feat && w && b && probs && k >= 1 && k <= 8, VIP_ERR_INVALID, "vip_head_f32: bad argument (1 <= k <= 8)");
-  head_kernel<<<(N * 32 + 127) / 128, 128, 0, ST(stream)>>>(feat, w, b, probs, acc, acc_weight, N, C, k, sigmoid_head);
+  VIP_LAUNCH((head_kernel), (N * 32 + 127) / 128, 128, 0, ST(stream), feat, w, b, probs, acc, acc_weight, N, C, k, sigmoid_head);
   LAUNCH_CHECK();
 }
 
 extern "C" int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* stream) {
   VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_f32_bf16: null pointer");
-  scale_cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, scale, (bf16*)out, n);
+  VIP_LAUNCH((scale_cast_f32_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), x, scale, (bf16*)out, n);
   LAUNCH_CHECK();
 }
 
 extern "C" int vip_cast_f32_bf16(const float* x, void* out, long long n, void* stream) {
   VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_cast_f32_bf16: null pointer");
-  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, (bf16*)out, n);
+  VIP_LAUNCH((cast_f32_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), x, (bf16*)out, n);
   LAUNCH_CHECK();
 }

@@ -313,6 +313,8 @@ __device__ __forceinline__ int trunc_small_float(float x) {    // (int)x for 0 <
 
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   float4* s_wy = reinterpret_cast<float4*>(smem + a.off_wy);
   short4* s_iy = reinterpret_cast<short4*>(smem + a.off_iy);
@@ -622,6 +624,8 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
 }
 
 __global__ void div255_selftest_kernel(unsigned long long* mismatches) {
+  pdl_trigger();
+  pdl_wait();
   const unsigned long long total = 1ull << 32;
   unsigned long long bad = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -694,7 +698,7 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   auto kern = dst_dtype == VIP_DTYPE_BF16 ? preprocess_kernel<true> : preprocess_kernel<false>;
   VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, off));
-  kern<<<N, kThreads, off, st>>>(a);
+  VIP_LAUNCH((kern), N, kThreads, off, st, a);
   VIP_CUDA(cudaGetLastError());
   count_launch();
   return VIP_OK;
@@ -707,7 +711,7 @@ extern "C" int vip_selftest_div255(uint64_t* mismatches, void* cuda_stream) {
   unsigned long long* d = nullptr;
   VIP_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
   VIP_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), st));
-  div255_selftest_kernel<<<148 * 8, 256, 0, st>>>(d);
+  VIP_LAUNCH((div255_selftest_kernel), 148 * 8, 256, 0, st, d);
   count_launch();
   unsigned long long hres = 0;
   cudaError_t e = cudaMemcpyAsync(&hres, d, sizeof(hres), cudaMemcpyDeviceToHost, st);
