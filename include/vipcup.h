@@ -170,6 +170,16 @@ int vip_window_attention_bf16(const void* qkv, const void* q_global, const float
 int vip_head_f32(const float* feat, const float* w, const float* b, float* probs, double* acc, double acc_weight, int N,
                  int C, int k, int sigmoid_head, void* cuda_stream);
 int vip_cast_f32_bf16(const float* x, void* out, long long n, void* cuda_stream);
+/* Fused pre-LN MLP of a GCViT block (models/gcvit/layers/block.py:39-56,77-81; layers/feature.py:8-43):
+ *   out[m, :] = x[m, :] + W2 gelu(W1 LayerNorm(x[m, :]) + b1) + b2     with LayerNorm folded like vip_epilogue_t.ln_stats:
+ *   ln_stats [M, 2] = (sum, sum of squares) of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,
+ *   colsum1 [hidden] their column sums, bias1 [hidden] = beta W1 + b1; w2 bf16 [C, ldw2], bias2 [C] (layer scale folded).
+ *   x, out bf16 [M, C] contiguous; row_stats [M, 2] (or NULL) receives (sum, sum of squares) of the rows of out.
+ * The hidden activations stay in TMEM / shared memory.  Built for (C, hidden) = (96, 192) and (64, 192); any other shape
+ * returns VIP_ERR_UNSUPPORTED and the caller issues two vip_gemm_bf16_ex calls instead. */
+int vip_mlp_fused_bf16(const void* x, long long M, int C, int hidden, const float* ln_stats, float ln_eps, const void* w1,
+                       int ldw1, const float* colsum1, const float* bias1, const void* w2, int ldw2, const float* bias2,
+                       void* out, float* row_stats, void* cuda_stream);
 /* out = bf16(x * scale): pooled sums of the fused gap epilogue -> means (SE squeeze, resnet_rs_model.py:149) */
 int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* cuda_stream);
 

@@ -151,3 +151,41 @@ def test_layernorm_matches_torch(cuda_device, m, c):
     gf = got.float()
     assert torch.allclose(stats[:, 0], gf.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(stats[:, 1], (gf * gf).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("m,c,hidden", [(128, 96, 192), (1000, 96, 192), (40000, 96, 192), (777, 64, 192), (128 * 149 + 5, 64, 192)])
+def test_mlp_fused_matches_two_gemms_and_torch(cuda_device, m, c, hidden):
+    """vip_mlp_fused_bf16 (block.py:39-56,77-81: x + fc2(gelu(fc1(LN(x)))), hidden tile kept in TMEM) against (1) the two
+    vip_gemm_bf16_ex calls it replaces on the same packed weights -- same arithmetic, so within one bf16 ulp of the output
+    -- and (2) fp32 torch with exact-erf GELU (tolerance 2e-2: bf16 hidden + fitted GELU).  Ragged M, more tiles than SMs."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(m + c)
+    x = (torch.randn((m, c), generator=g) * 1.5 + 0.2).to(torch.bfloat16).to(cuda_device)
+    gamma, beta = torch.rand((c,), generator=g) + 0.5, torch.randn((c,), generator=g) * 0.2
+    k1 = torch.randn((c, hidden), generator=g) / c ** 0.5
+    b1 = torch.randn((hidden,), generator=g) * 0.1
+    k2 = torch.randn((hidden, c), generator=g) / hidden ** 0.5
+    b2 = torch.randn((c,), generator=g) * 0.1
+    w1 = (k1 * gamma[:, None]).T.contiguous().to(torch.bfloat16)            # [hidden, c], gamma folded
+    colsum1 = w1.float().sum(1).to(cuda_device)
+    bias1 = (beta @ k1 + b1).to(cuda_device)
+    w1 = w1.to(cuda_device)
+    w2 = k2.T.contiguous().to(torch.bfloat16).to(cuda_device)               # [c, hidden]
+    bias2 = b2.to(cuda_device)
+    xf = x.float()
+    stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
+    rs_f = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
+    got = nn.mlp_fused(x, stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=rs_f)
+    hdn = nn.gemm(x, w1, bias=bias1, act="gelu", ln_stats=stats, ln_colsum=colsum1, ln_cols=c, ln_eps=1e-5)
+    rs_g = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
+    two = nn.gemm(hdn, w2, bias=bias2, residual=x, row_stats=rs_g)
+    torch.cuda.synchronize()
+    d = (got.float() - two.float()).abs()
+    assert (d <= two.float().abs() * 2.0 ** -7 + 1e-3).all(), d.max().item()
+    assert torch.allclose(rs_f, rs_g, rtol=2e-3, atol=5e-2)
+    ln = torch.nn.functional.layer_norm(xf.cpu(), (c,), gamma, beta, 1e-5)
+    ref = xf.cpu() + torch.nn.functional.gelu(ln @ k1 + b1) @ k2 + b2
+    assert (got.float().cpu() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())

@@ -12,6 +12,8 @@ Layer -> kernel:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -32,6 +34,9 @@ def _rel_index(ws):  # attention.py:39-50
     coords = np.stack(np.meshgrid(np.arange(ws), np.arange(ws), indexing="ij")).reshape(2, -1)
     rel = coords[:, :, None] - coords[:, None, :]
     return (rel[0] + ws - 1) * (2 * ws - 1) + (rel[1] + ws - 1)
+
+
+FUSED_MLP = os.environ.get("VIP_FUSED_MLP", "1") != "0"   # level-0 MLPs through vip_mlp_fused_bf16
 
 
 def _pad_rows(a, mult=32):  # [N, K] -> N rounded up to `mult` with zero rows
@@ -235,8 +240,12 @@ class GCViT:
         a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
         x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=st_mid)
         w1, b1, c1 = d["fc1"]
-        hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
-        x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out)
+        if FUSED_MLP and (c, w1.shape[0]) in nn.MLP_FUSED_SHAPES:
+            # narrow levels: both contractions in one kernel, the [tokens, hidden] tensor never reaches HBM
+            x2 = nn.mlp_fused(x2, st_mid, w1, c1, b1, *d["fc2"], ln_eps=LN_EPS, row_stats=st_out)
+        else:
+            hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
+            x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out)
         return x2.view(b, h, w, c)
 
     def features(self, x, taps=None):

@@ -205,6 +205,24 @@ def cast_bf16(x_f32):
     return out
 
 
+MLP_FUSED_SHAPES = {(96, 192), (64, 192)}
+
+
+def mlp_fused(x, ln_stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=None):
+    """x + fc2(gelu(fc1(LayerNorm(x)))) in one kernel (hidden activations stay on the SM); arguments as for the two
+    ``gemm`` calls it replaces: w1 [hidden, C] gamma-scaled + colsum1 + bias1 (LayerNorm folded), w2 [C, hidden] + bias2.
+    Only for (C, hidden) in MLP_FUSED_SHAPES."""
+    _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2"), _chk(ln_stats, "ln_stats", torch.float32)
+    m, c = x.shape
+    hidden = w1.shape[0]
+    out = torch.empty_like(x)
+    rc = _lib.lib().vip_mlp_fused_bf16(_p(x), m, c, hidden, _p(ln_stats), float(ln_eps), _p(w1), w1.stride(0), _p(colsum1),
+                                       _p(bias1), _p(w2), w2.stride(0), _p(bias2), _p(out),
+                                       _p(row_stats) if row_stats is not None else None, _st())
+    _lib.check(rc, "vip_mlp_fused_bf16")
+    return out
+
+
 def scale_cast_bf16(x_f32, scale):
     _chk(x_f32, "x", torch.float32)
     out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
