@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
 
 #include "common.cuh"
 
@@ -117,6 +118,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmov.b64 rc, {%6,%7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// gelu_fast on a pair (packed fp32: half the issue slots)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 x2 = fmul2(x, x);
+  x2.x = fminf(x2.x, 64.0f);
+  x2.y = fminf(x2.y, 64.0f);
+  float2 p = ffma2(make_float2(-0.00035307545f, -0.00035307545f), x2, make_float2(0.037015257f, 0.037015257f));
+  p = ffma2(p, x2, make_float2(0.79749725f, 0.79749725f));
+  const float2 u = fmul2(p, x);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, t, hx);
+}
 // same fitted tanh form as the GEMM epilogue (gemm.cu: gelu_fast)
 __device__ __forceinline__ float gelu_fast(float x) {
   const float x2 = fminf(x * x, 64.0f);
@@ -127,6 +157,12 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+
+#ifdef VIP_MLP_TRACE
+// bring-up aid (VIP_NVCC_EXTRA=-DVIP_MLP_TRACE): cycles of epilogue group 0, thread 0 of CTA 0, summed over its tiles:
+// [0] tiles, [1] wait for H, [2] pass 1, [3] wait for Y, [4] pass 2
+__device__ long long g_mlp_trace[8];
+#endif
 
 template <int C, int HD>
 struct MlpCfg {
@@ -265,16 +301,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const float invC = 1.0f / (float)C;
     uint32_t job = 0;
     int n = g;
+    auto load_stats = [&](int tile_) -> float2 {
+      const long long m_ = (long long)tile_ * 128 + row;
+      return tile_ < total_tiles && m_ < a.M ? __ldg(reinterpret_cast<const float2*>(a.ln_stats) + m_) : make_float2(0.0f, 0.0f);
+    };
+    float2 st_next = load_stats(blockIdx.x + g * gridDim.x);
     for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, n += 2, ++job) {
       const int s = n % kStages;
       const long long m = (long long)tile * 128 + row;
       const bool row_ok = m < a.M;
-      const float2 st = row_ok ? __ldg(reinterpret_cast<const float2*>(a.ln_stats) + m) : make_float2(0.0f, 0.0f);
+      const float2 st = st_next;
+      st_next = load_stats(tile + 2 * gridDim.x);   // in flight during this tile
       const float mean = st.x * invC;
       const float rstd = rsqrtf(fmaxf(st.y * invC - mean * mean, 0.0f) + a.ln_eps);
       const float nmr = -mean * rstd;
+#ifdef VIP_MLP_TRACE
+      const long long t0 = clock64();
+#endif
       mbar_wait(h_full + g, job & 1u);
       tc_fence_after();
+#ifdef VIP_MLP_TRACE
+      const long long t1 = clock64();
+#endif
       // ---- pass 1: hidden = gelu(rstd (acc - mean colsum) + bias) -> packed bf16 over the consumed columns of H
       {
         uint32_t r[2][32];
@@ -287,9 +335,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 p0 = sP1[c * 32 + i], p1 = sP1[c * 32 + i + 1];
-            const float v0 = gelu_fast(fmaf(__uint_as_float(r[c & 1][i]), rstd, fmaf(nmr, p0.x, p0.y)));
-            const float v1 = gelu_fast(fmaf(__uint_as_float(r[c & 1][i + 1]), rstd, fmaf(nmr, p1.x, p1.y)));
-            pk[i >> 1] = pack_bf16(v0, v1);
+            const float2 sh = ffma2(make_float2(nmr, nmr), make_float2(p0.x, p1.x), make_float2(p0.y, p1.y));
+            const float2 v = gelu_fast2(ffma2(make_float2(__uint_as_float(r[c & 1][i]), __uint_as_float(r[c & 1][i + 1])),
+                                              make_float2(rstd, rstd), sh));
+            pk[i >> 1] = pack_bf16(v.x, v.y);
           }
           tmem_st16(tl + c * 16, pk);
         }
@@ -297,31 +346,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(h2_full + g);
+#ifdef VIP_MLP_TRACE
+      const long long t2 = clock64();
+#endif
       // ---- pass 2: y = acc + bias + x -> bf16 -> global; statistics of the output row
       mbar_wait(y_full + g, job & 1u);
       tc_fence_after();
+#ifdef VIP_MLP_TRACE
+      const long long t3 = clock64();
+#endif
       float rs_sum = 0.0f, rs_sq = 0.0f;
       const uint8_t* xrow = sX + s * Cfg::kXBytes + row * 128;
       bf16* orow = a.out + m * C;
+      uint32_t ry[C / 32][32];
+#pragma unroll
+      for (int c = 0; c < C / 32; ++c) tmem_ld32_nowait(tl + Cfg::Y_COL + c * 32, ry[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(y_free + g);      // Y is in registers: the next H may overwrite it
 #pragma unroll
       for (int c = 0; c < C / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32_nowait(tl + Cfg::Y_COL + c * 32, r);
-        tmem_ld_wait();
-        if (c == C / 32 - 1) {   // Y is in registers: the next H may overwrite it
-          tc_fence_before();
-          mbar_arrive(y_free + g);
-        }
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
           const int col = c * 32 + q8 * 8;            // first of 8 channels; k-block col / 64, 16-byte chunk (col % 64) / 8
           const uint4 xr = *reinterpret_cast<const uint4*>(xrow + (col >> 6) * 16384 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
           const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+          const float4 ba = *reinterpret_cast<const float4*>(sB2 + col), bb = *reinterpret_cast<const float4*>(sB2 + col + 4);
+          const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t w[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float v0 = __uint_as_float(r[q8 * 8 + 2 * t]) + sB2[col + 2 * t] + __uint_as_float(xw[t] << 16);
-            const float v1 = __uint_as_float(r[q8 * 8 + 2 * t + 1]) + sB2[col + 2 * t + 1] + __uint_as_float(xw[t] & 0xffff0000u);
+            const float v0 = __uint_as_float(ry[c][q8 * 8 + 2 * t]) + bs[2 * t] + __uint_as_float(xw[t] << 16);
+            const float v1 = __uint_as_float(ry[c][q8 * 8 + 2 * t + 1]) + bs[2 * t + 1] + __uint_as_float(xw[t] & 0xffff0000u);
             rs_sum += v0 + v1;
             rs_sq = fmaf(v0, v0, rs_sq);
             rs_sq = fmaf(v1, v1, rs_sq);
@@ -332,6 +388,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       mbar_arrive(empty + s);   // the residual has been read: the stage may be refilled
       if (a.row_stats != nullptr && row_ok) *reinterpret_cast<float2*>(a.row_stats + 2 * m) = make_float2(rs_sum, rs_sq);
+#ifdef VIP_MLP_TRACE
+      if (blockIdx.x == 0 && tid == 0) {
+        const long long t4 = clock64();
+        g_mlp_trace[0] += 1;
+        g_mlp_trace[1] += t1 - t0;
+        g_mlp_trace[2] += t2 - t1;
+        g_mlp_trace[3] += t3 - t2;
+        g_mlp_trace[4] += t4 - t3;
+      }
+#endif
     }
   }
   tc_fence_before();
@@ -392,6 +458,18 @@ int launch_mlp(const bf16* x, long long M, const bf16* w1, int ldw1, const bf16*
   VIP_LAUNCH(kern, grid, Cfg::kThreads, Cfg::kSmem, st, tmX, tmW1, tmW2, a);
   VIP_CUDA(cudaGetLastError());
   count_launch();
+#ifdef VIP_MLP_TRACE
+  {
+    long long t[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(t, g_mlp_trace, sizeof(t));
+    if (t[0] > 0)
+      fprintf(stderr, "[mlp trace %d/%d] tiles %lld  wait H %lld  pass 1 %lld  wait Y %lld  pass 2 %lld cycles/tile\n", C, HD, t[0],
+              t[1] / t[0], t[2] / t[0], t[3] / t[0], t[4] / t[0]);
+    long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_mlp_trace, z, sizeof(z));
+  }
+#endif
   return VIP_OK;
 }
 
