@@ -170,6 +170,14 @@ int vip_window_attention_bf16(const void* qkv, const void* q_global, const float
 int vip_head_f32(const float* feat, const float* w, const float* b, float* probs, double* acc, double acc_weight, int N,
                  int C, int k, int sigmoid_head, void* cuda_stream);
 int vip_cast_f32_bf16(const float* x, void* out, long long n, void* cuda_stream);
+/* vip_gemm_bf16_ex with one weight matrix per group of rows: rows [i * rows_per_group, (i + 1) * rows_per_group) of A are
+ * contracted with B[i * N : (i + 1) * N, :] (B is [ceil(M / rows_per_group) * N, ldb]).  rows_per_group must be a multiple
+ * of 128.  Used to fold a per-image input-channel scale (the SE gate of an MBConv block, feature.py:144-150) into the
+ * weights of the 1x1 convolution that follows, built by vip_scale_weights_bf16. */
+int vip_gemm_grouped_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int rows_per_group,
+                          const vip_epilogue_t* epilogue, void* cuda_stream);
+/* out[g][n][k] = bf16(w[n][k] * gate[g][k]); w bf16 [N, ldw], gate fp32 [G, K], out bf16 [G * N, K] */
+int vip_scale_weights_bf16(const void* w, int ldw, const float* gate, int G, int N, int K, void* out, void* cuda_stream);
 /* Fused pre-LN MLP of a GCViT block (models/gcvit/layers/block.py:39-56,77-81; layers/feature.py:8-43):
  *   out[m, :] = x[m, :] + W2 gelu(W1 LayerNorm(x[m, :]) + b1) + b2     with LayerNorm folded like vip_epilogue_t.ln_stats:
  *   ln_stats [M, 2] = (sum, sum of squares) of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,

@@ -189,3 +189,26 @@ def test_mlp_fused_matches_two_gemms_and_torch(cuda_device, m, c, hidden):
     ln = torch.nn.functional.layer_norm(xf.cpu(), (c,), gamma, beta, 1e-5)
     ref = xf.cpu() + torch.nn.functional.gelu(ln @ k1 + b1) @ k2 + b2
     assert (got.float().cpu() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("groups,rows,n,k", [(3, 128, 96, 96), (5, 256, 64, 64), (2, 12544, 96, 96), (7, 384, 192, 192)])
+def test_gemm_grouped_folds_a_per_image_input_scale(cuda_device, groups, rows, n, k):
+    """vip_scale_weights_bf16 + vip_gemm_grouped_bf16 (SE gate of an MBConv block folded into per-image copies of the 1x1
+    convolution weights, feature.py:144-150) against fp32 torch on (y * gate_image) @ W^T + residual."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(groups * 1000 + rows)
+    m = groups * rows
+    y = torch.randn((m, k), generator=g).to(torch.bfloat16).to(cuda_device)
+    res = torch.randn((m, n), generator=g).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn((n, k), generator=g) / k ** 0.5).to(torch.bfloat16).to(cuda_device)
+    gate = torch.rand((groups, k), generator=g).to(cuda_device)
+    wg = nn.scale_weights(w, gate)
+    got = nn.gemm_grouped(y, wg, rows, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(wg.float().view(groups, n, k), (w.float()[None] * gate[:, None, :]).to(torch.bfloat16).float())
+    ref = torch.einsum("gmk,gnk->gmn", y.float().view(groups, rows, k), wg.float().view(groups, n, k)).reshape(m, n) + res.float()
+    err = (got.float() - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 2e-3).all(), err.max().item()

@@ -50,6 +50,9 @@ struct GemmArgs {
   // patch tiles (conv == 2): a tile is bni images x bh rows x bw columns of the output (<= 128 pixels)
   int bw, bh, bni, tiles_w, tiles_h, prow, Ho, Nimg;
   int mode;  // EpiMode
+  // grouped B (plain GEMM only): rows [i * bgroup_mtiles * 128, ...) of A are contracted with rows
+  // [i * bgroup_rows, (i + 1) * bgroup_rows) of B -- one weight matrix per image (0 = one B for all rows)
+  int bgroup_mtiles, bgroup_rows;
   int dbg;            // experiments: 4 = MMA warp does not wait for operands, 8 = MMA warp issues no MMAs
   long long* trace;  // VIP_GEMM_TRACE=1: per-tile clock64() stamps of CTA 0 ([tile][8]); null otherwise
   GemmEpilogue epi;
@@ -533,7 +536,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], tap * g.C + cb * BK, n0);
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, m0);
-            tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0);
+            const int brow = g.bgroup_mtiles > 0 ? ((tile / g.n_tiles) / g.bgroup_mtiles) * g.bgroup_rows : 0;
+            tma_load_2d(a_dst + kABytes, &tmB, &full_bar[s], kb * BK, n0 + brow);
           }
         }
         if (g.trace != nullptr && blockIdx.x == 0) g.trace[(tile / cta_tile_step) * 16 + 1] = clock64();
@@ -1019,7 +1023,7 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
 }
 
 int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, int N, int K, GemmArgs& g,
-        const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* tmC_patch = nullptr) {
+        const GemmEpilogue& epi, cudaStream_t stream, const CUtensorMap* tmC_patch = nullptr, int rows_per_group = 0) {
   VIP_REQUIRE(N <= kMaxCols, VIP_ERR_UNSUPPORTED, "gemm: N = %d exceeds %d", N, kMaxCols);
   int rc0 = ensure_neutral(stream);
   if (rc0 != VIP_OK) return rc0;
@@ -1034,10 +1038,16 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   // Measured (profiles/README.md): 76 % of the cuBLAS peak at 8192^3 against 71 % for one CTA per tile, but no gain below
   // K ~ 4096, where the tile prologue and the epilogue dominate: enabled for long K loops only.
   static const int pair_min_kb = [] { const char* v = getenv("VIP_GEMM_PAIR_MIN_KB"); return v != nullptr ? atoi(v) : 64; }();
-  const bool pair = pair_env && deep && g.conv == 0 && M >= 2 * BM && N >= 128 && g.num_kb >= pair_min_kb;
+  const bool pair = pair_env && deep && g.conv == 0 && M >= 2 * BM && N >= 128 && g.num_kb >= pair_min_kb && rows_per_group == 0;
   if (pair && bn < 128) bn = 128;
+  long long b_rows = N;
+  if (rows_per_group > 0) {   // one [N, K] weight matrix per group of rows_per_group rows of A
+    g.bgroup_mtiles = rows_per_group / BM;
+    g.bgroup_rows = N;
+    b_rows = (long long)N * ((M + rows_per_group - 1) / rows_per_group);
+  }
   CUtensorMap tmB, tmC, tmR;
-  int rc = make_tmap_2d(&tmB, B, N, K, ldb, pair ? bn / 2 : bn);
+  int rc = make_tmap_2d(&tmB, B, b_rows, K, ldb, pair ? bn / 2 : bn);
   if (rc != VIP_OK) return rc;
   tmC = tmB;
   tmR = tmB;
@@ -1112,8 +1122,10 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
 }  // namespace
 
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
-              const GemmEpilogue& epi, cudaStream_t stream) {
+              const GemmEpilogue& epi, cudaStream_t stream, int rows_per_group) {
   VIP_REQUIRE(M > 0 && N > 0 && K > 0, VIP_ERR_INVALID, "gemm_bf16: empty problem %dx%dx%d", M, N, K);
+  VIP_REQUIRE(rows_per_group >= 0 && rows_per_group % BM == 0, VIP_ERR_UNSUPPORTED,
+              "gemm_bf16: rows_per_group = %d must be a multiple of %d (tiles may not straddle weight groups)", rows_per_group, BM);
   VIP_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, VIP_ERR_UNSUPPORTED,
               "gemm_bf16: K, lda, ldb must be multiples of 8 (16-byte TMA rows): K=%d lda=%d ldb=%d", K, lda, ldb);
   VIP_REQUIRE(N % 8 == 0, VIP_ERR_UNSUPPORTED, "gemm_bf16: N must be a multiple of 8 (N=%d)", N);
@@ -1125,7 +1137,7 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, 
   if (rc != VIP_OK) return rc;
   GemmArgs g{};
   g.num_kb = (K + BK - 1) / BK;
-  return run(tmA, B, ldb, M, N, K, g, epi, stream);
+  return run(tmA, B, ldb, M, N, K, g, epi, stream, nullptr, rows_per_group);
 }
 
 int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* w, int ldw, int Cout,
@@ -1264,6 +1276,14 @@ extern "C" int vip_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, 
   VIP_REQUIRE(A && B && epi && epi->out, VIP_ERR_INVALID, "vip_gemm_bf16_ex: null pointer");
   return vip::gemm_bf16(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb,
                         M, N, K, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int vip_gemm_grouped_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int rows_per_group,
+                                     const vip_epilogue_t* epi, void* cuda_stream) {
+  VIP_REQUIRE(A && B && epi && epi->out, VIP_ERR_INVALID, "vip_gemm_grouped_bf16: null pointer");
+  VIP_REQUIRE(rows_per_group > 0, VIP_ERR_INVALID, "vip_gemm_grouped_bf16: rows_per_group must be positive");
+  return vip::gemm_bf16(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb,
+                        M, N, K, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream), rows_per_group);
 }
 
 extern "C" int vip_conv2d_bf16(const void* x, int N, int H, int W, int C, const void* w, int ldw, int Cout, int ksize,

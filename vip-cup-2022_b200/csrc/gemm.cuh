@@ -49,8 +49,9 @@ struct ConvGeom {
 
 // A: [M, K] row-major bf16 (lda elements between rows), B: [N, K] row-major bf16 (ldb).  K, N, lda, ldb, ldc, ldr
 // multiples of 8, 16-byte aligned bases.  Enqueues on `stream`; returns VIP_OK or a negative error code.
+// rows_per_group > 0 (a multiple of 128): B holds one [N, K] matrix per group of rows_per_group rows of A, stacked.
 int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K,
-              const GemmEpilogue& epi, cudaStream_t stream);
+              const GemmEpilogue& epi, cudaStream_t stream, int rows_per_group = 0);
 
 // Implicit-GEMM convolution: x bf16 NHWC, weights bf16 [Cout, ksize*ksize*C] (K order r, s, c = Keras (kh,kw,Cin,Cout)
 // flattened over its first three axes, ldw elements between rows), output rows = N*Ho*Wo pixels.  C % 8 == 0.

@@ -644,6 +644,22 @@ __global__ void scale_cast_f32_bf16_kernel(const float* __restrict__ x, float sc
     out[i] = __float2bfloat16_rn(x[i] * scale);
 }
 
+// ---- out[g][n][k] = bf16(w[n][k] * gate[g][k]): the SE gate of an MBConv block (feature.py:49-66,144-150) scales the INPUT
+// channels of the 1x1 convolution that follows, y .* gate_g -> W; per image that is the same as contracting y with
+// W diag(gate_g), so the gate is folded into per-image copies of the (tiny) weight matrix instead of a pass over y.
+__global__ void scale_weights_kernel(const bf16* __restrict__ w, int ldw, const float* __restrict__ gate, bf16* __restrict__ out,
+                                     int G, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)G * N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const long long t = i / K;
+    const int n = (int)(t % N), gi = (int)(t / N);
+    out[i] = __float2bfloat16_rn(__bfloat162float(w[(long long)n * ldw + k]) * gate[(long long)gi * K + k]);
+  }
+}
+
 }  // namespace
 }  // namespace vip
 
@@ -743,6 +759,13 @@ extern "C" int vip_head_f32(const float* feat, const float* w, const float* b, f
 extern "C" int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* stream) {
   VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_f32_bf16: null pointer");
   VIP_LAUNCH((scale_cast_f32_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), x, scale, (bf16*)out, n);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_scale_weights_bf16(const void* w, int ldw, const float* gate, int G, int N, int K, void* out, void* stream) {
+  VIP_REQUIRE(w && gate && out && G > 0 && N > 0 && K > 0 && ldw >= K, VIP_ERR_INVALID, "vip_scale_weights_bf16: bad argument");
+  VIP_LAUNCH((scale_weights_kernel), grid_for((long long)G * N * K, 256), 256, 0, ST(stream), (const bf16*)w, ldw, gate, (bf16*)out, G,
+             N, K);
   LAUNCH_CHECK();
 }
 

@@ -221,6 +221,11 @@ class GCViT:
         pooled = nn.scale_cast_bf16(gap, 1.0 / (h * w))
         hid = nn.gemm(pooled, d["fc0"], act="gelu")
         gate = nn.gemm(hid, d["fc2"], act="sigmoid", out_dtype=torch.float32)
+        if (h * w) % 128 == 0 and d["pw"].shape[1] == c:
+            # the gate scales the input channels of the 1x1 convolution: fold it into per-image copies of the (C x C)
+            # weights instead of a read-modify-write pass over y (whole 128-row tiles per image required)
+            wg = nn.scale_weights(d["pw"], gate)
+            return nn.gemm_grouped(y.view(-1, c), wg, h * w, residual=x.view(-1, c)).view(b, h, w, c)
         y = nn.scale_add_act(y, gate, None, out=y)
         return nn.gemm(y.view(-1, c), d["pw"], residual=x.view(-1, c)).view(b, h, w, c)
 

@@ -60,6 +60,33 @@ def gemm(a, w, bias=None, act=None, colscale=None, residual=None, out=None, out_
     return out
 
 
+def gemm_grouped(a, w, rows_per_group, bias=None, act=None, residual=None, out=None, **fused):
+    """``gemm`` with one weight matrix per group of ``rows_per_group`` rows of ``a`` (a multiple of 128):
+    w is [groups * N, K], group i of the rows is contracted with w[i * N : (i + 1) * N]."""
+    _chk(a, "a"), _chk(w, "w")
+    m, k = a.shape
+    groups = (m + rows_per_group - 1) // rows_per_group
+    n = w.shape[0] // groups
+    if w.shape[1] != k or n * groups != w.shape[0]:
+        raise VipError(f"gemm_grouped: {tuple(a.shape)} x {tuple(w.shape)} with {groups} groups")
+    if out is None:
+        out = torch.empty((m, n), dtype=BF16, device=a.device)
+    e = _epilogue(out, bias, act, None, residual, **fused)
+    rc = _lib.lib().vip_gemm_grouped_bf16(_p(a), a.stride(0), _p(w), w.stride(0), m, n, k, rows_per_group, e, _st())
+    _lib.check(rc, "vip_gemm_grouped_bf16")
+    return out
+
+
+def scale_weights(w, gate):
+    """[G * N, K] bf16 = w[n, k] * gate[g, k]: a per-image input-channel scale folded into copies of the weights."""
+    _chk(w, "w"), _chk(gate, "gate", torch.float32)
+    n, k = w.shape
+    g = gate.shape[0]
+    out = torch.empty((g * n, k), dtype=BF16, device=w.device)
+    _lib.check(_lib.lib().vip_scale_weights_bf16(_p(w), w.stride(0), _p(gate), g, n, k, _p(out), _st()), "vip_scale_weights_bf16")
+    return out
+
+
 def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, **fused):
     """x bf16 [N,H,W,C]; w bf16 [Cout, Kp] with K order (r,s,c). Returns bf16 [N,Ho,Wo,Cout].
     1x1 stride 1: plain GEMM on the NHWC activation; C % 8 == 0: implicit GEMM (im2col-mode TMA, nothing materialised);
