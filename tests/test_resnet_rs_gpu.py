@@ -58,3 +58,27 @@ def test_resnet_rs_matches_oracle(cuda_device, depth, head):
     torch.cuda.synchronize()
     check_against_oracle(ref, ref_taps, got, taps, W["predictions/kernel"], W["predictions/bias"],
                          ("stem", "c2", "c3", "c4", "c5"))
+
+
+def test_predict_host_many_pipeline_matches_single_calls(cuda_device):
+    """EnsemblePredictor.predict_host_many (H2D of batch i + 1 on a copy stream under the graph of batch i, two staging
+    buffers) returns for every batch exactly what predict_host returns for it alone: five distinct batches, so that each
+    staging buffer is reused and a stale or early copy would show."""
+    import torch
+
+    from oracle import preprocess as P
+    from oracle import resnet_rs as R
+    from vipcup_b200.models import ResNetRS
+    from vipcup_b200.predict import EnsemblePredictor
+
+    W = R.random_weights(50, 2, seed=3)
+    model = ResNetRS(50, classes=2, classifier_activation="softmax", device=cuda_device).load_weights(W)
+    B = 4
+    pred = EnsemblePredictor([(model, (200, 200))], B, src_hw=(200, 200), device=cuda_device)
+    batches = [torch.from_numpy(np.stack([P.synth_image(10 * j + i) for i in range(B)])).pin_memory() for j in range(5)]
+    singles = [pred.predict_host(b).clone() for b in batches]
+    outs = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in batches]
+    pred.predict_host_many(batches, outs)
+    for a, b in zip(singles, outs):
+        assert torch.equal(a, b)
+    assert not torch.equal(outs[0], outs[1])

@@ -198,3 +198,39 @@ class EnsemblePredictor:
         out_host.copy_(self.acc, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return out_host
+
+    def predict_host_many(self, batches, outs, flags=None):
+        """A sequence of pinned host uint8 batches -> pinned host float64 [B] each, pipelined: the host-to-device copy of
+        batch i + 1 runs on a copy stream into one of two staging buffers while the graph of batch i executes (what the
+        reference gets from tf.data prefetch, dataset/dataset.py:100).  Returns after the last result has landed."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty_like(self.src), torch.empty_like(self.src)]
+            self._ev_h2d = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        cs, stage, ev_h2d, ev_free = self._copy_stream, self._stage, self._ev_h2d, self._ev_free
+        n = len(batches)
+        if n == 0:
+            return outs
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            stage[0].copy_(batches[0], non_blocking=True)
+            ev_h2d[0].record(cs)
+        for i in range(n):
+            if i + 1 < n:
+                with torch.cuda.stream(cs):
+                    if i >= 1:
+                        cs.wait_event(ev_free[(i + 1) & 1])   # staging buffer consumed by step i - 1
+                    stage[(i + 1) & 1].copy_(batches[i + 1], non_blocking=True)
+                    ev_h2d[(i + 1) & 1].record(cs)
+            main.wait_event(ev_h2d[i & 1])
+            self.src.copy_(stage[i & 1], non_blocking=True)
+            ev_free[i & 1].record(main)
+            if flags is not None:
+                self.flags.copy_(flags[i], non_blocking=True)
+            self.run()
+            outs[i].copy_(self.acc, non_blocking=True)
+        main.synchronize()
+        return outs
