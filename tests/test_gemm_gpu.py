@@ -131,7 +131,7 @@ def test_dwconv_fused_squeeze(cuda_device):
 
 @pytest.mark.parametrize("m,c", [(1000, 64), (4099, 96), (777, 128), (513, 192), (300, 384), (65, 768)])
 def test_layernorm_matches_torch(cuda_device, m, c):
-    """vip_layernorm_bf16 (block.py:28,39; feature.py:100-101; gcvit.py:79): thread-per-row kernel for C <= 128, lane-group
+    """vip_layernorm_bf16 (block.py:28,39; feature.py:100-101; gcvit.py:79): 4-lane rows for C <= 128, 32-lane rows
     kernel above, against fp32 torch on the same bf16 input; row_stats = (sum, sum of squares) of the ROUNDED output rows.
     Tolerance: one bf16 ulp of the output (2^-8 relative) + 1e-3."""
     import torch

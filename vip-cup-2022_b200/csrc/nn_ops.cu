@@ -233,74 +233,9 @@ __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __
   }
 }
 
-// ---- LayerNormalization for narrow rows (C <= 128): ONE THREAD PER ROW.  The lane-group kernel below keeps 16 bytes per
-// lane in flight and needs two shuffle reductions per row (2.6 TB/s at C = 96); here a thread has its whole row (NC8
-// 16-byte loads) in flight, reduces in registers, and a warp covers 32 consecutive rows = one contiguous span.
-template <int NC8>
-__global__ void __launch_bounds__(128) layernorm_row_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, bf16* __restrict__ out,
-                                                            float* __restrict__ row_stats, long long M, float eps) {
-  pdl_trigger();
-  pdl_wait();
-  constexpr int C = NC8 * 8;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const uint4* src = reinterpret_cast<const uint4*>(x + m * C);
-  uint4 raw[NC8];
-#pragma unroll
-  for (int j = 0; j < NC8; ++j) raw[j] = __ldg(src + j);
-  float f[NC8][8];
-  float s = 0.0f;
-#pragma unroll
-  for (int j = 0; j < NC8; ++j) {
-    const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      f[j][2 * q] = __uint_as_float(w[q] << 16);
-      f[j][2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-      s += f[j][2 * q] + f[j][2 * q + 1];
-    }
-  }
-  const float mean = s * (1.0f / C);
-  float v = 0.0f;
-#pragma unroll
-  for (int j = 0; j < NC8; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float d = f[j][k] - mean;
-      v = fmaf(d, d, v);
-    }
-  const float rstd = rsqrtf(v * (1.0f / C) + eps);
-  float os = 0.0f, oq = 0.0f;
-  uint4* dst = reinterpret_cast<uint4*>(out + m * C);
-#pragma unroll
-  for (int j = 0; j < NC8; ++j) {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + j * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + j * 8) + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + j * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + j * 8) + 1);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float o8[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[j][k] - mean) * rstd, gg[k], bb[k]);
-    const bf16x8 pk = pack8(o8);
-    dst[j] = *reinterpret_cast<const uint4*>(&pk);
-    if (row_stats != nullptr) {
-      float r8[8];
-      unpack8(pk, r8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        os += r8[k];
-        oq = fmaf(r8[k], r8[k], oq);
-      }
-    }
-  }
-  if (row_stats != nullptr) *reinterpret_cast<float2*>(row_stats + 2 * m) = make_float2(os, oq);
-}
-
 // ---- LayerNormalization(axis=-1, eps) over [M, C] (block.py:28,39; feature.py:100-101; gcvit.py:79).  A row is handled
 // by LPR lanes (8, 16 or 32, so that narrow rows do not idle most of a warp), J 16-byte chunks per lane.
-// U row groups per warp iteration can be loaded before any of them is reduced; measured at [12.8 M, 96]: U = 4 (74
-// registers, 3 blocks per SM) 1.99 ms against 1.51 ms for U = 1 (8 blocks per SM), so U = 1 is what is launched.
+// U row groups per warp iteration are loaded before any of them is reduced.
 template <int LPR, int J, int U>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
@@ -720,12 +655,11 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
   bf16* op = (bf16*)out;
   const int c8n = C / 8;
   cudaStream_t st = ST(stream);
-  const unsigned rgrid = (unsigned)((M + 127) / 128);
-  if (c8n == 8) VIP_LAUNCH((layernorm_row_kernel<8>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n == 12) VIP_LAUNCH((layernorm_row_kernel<12>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n == 16) VIP_LAUNCH((layernorm_row_kernel<16>), rgrid, 128, 0, st, xp, gamma, beta, op, row_stats, M, eps);
-  else if (c8n <= 8) VIP_LAUNCH((layernorm_kernel<8, 1, 1>), grid_for(M * 8, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 16) VIP_LAUNCH((layernorm_kernel<16, 1, 1>), grid_for(M * 16, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  // narrow rows (C <= 128): 4 lanes per row (64 contiguous bytes per row and instruction), two row groups in flight.
+  // Measured at [12.8 M, 96] on B200: 16 lanes per row 1.51 ms, one thread per row 1.42, 4 lanes 1.19, 4 lanes x 2 groups 1.12.
+  if (c8n <= 8) VIP_LAUNCH((layernorm_kernel<4, 2, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 12) VIP_LAUNCH((layernorm_kernel<4, 3, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  else if (c8n <= 16) VIP_LAUNCH((layernorm_kernel<4, 4, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
   else if (c8n <= 32) VIP_LAUNCH((layernorm_kernel<32, 1, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
   else if (c8n <= 64) VIP_LAUNCH((layernorm_kernel<32, 2, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
   else VIP_LAUNCH((layernorm_kernel<32, 4, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
