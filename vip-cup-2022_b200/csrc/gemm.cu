@@ -53,9 +53,6 @@ struct GemmArgs {
   // grouped B (plain GEMM only): rows [i * bgroup_mtiles * 128, ...) of A are contracted with rows
   // [i * bgroup_rows, (i + 1) * bgroup_rows) of B -- one weight matrix per image (0 = one B for all rows)
   int bgroup_mtiles, bgroup_rows;
-  // 16-element K steps that hold data in the LAST k-block of the contraction (GEMM) / of every filter tap (convolution):
-  // K or C that is not a multiple of 64 leaves the tail of that k-block zero-filled, and its MMAs are skipped
-  int last_kb_steps;
   int dbg;            // experiments: 4 = MMA warp does not wait for operands, 8 = MMA warp issues no MMAs
   long long* trace;  // VIP_GEMM_TRACE=1: per-tile clock64() stamps of CTA 0 ([tile][8]); null otherwise
   GemmEpilogue epi;
@@ -601,21 +598,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
           const uint64_t a_desc = make_sw128_desc(a_addr);
           const uint64_t b_desc = make_sw128_desc(a_addr + kABytes);
-          int nsteps = BK / 16;
-          if (g.conv) {
-            if (g.cblocks > 1 && kb % g.cblocks == g.cblocks - 1) nsteps = g.last_kb_steps;
-            else if (g.cblocks == 1) nsteps = g.last_kb_steps;
-          } else if (kb == g.num_kb - 1) {
-            nsteps = g.last_kb_steps;
-          }
-          if (g.dbg & 8) nsteps = 0;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if (k < nsteps) {
-              // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-              if (kPair) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            if (g.dbg & 8) break;
+            // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+            if (kPair) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc_pair, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // implies tcgen05.fence::before_thread_sync; pair mode: releases the ring slot in BOTH CTAs
           if (kPair) umma_commit_pair(&empty_bar[s]);
@@ -1149,7 +1137,6 @@ int gemm_bf16(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, 
   if (rc != VIP_OK) return rc;
   GemmArgs g{};
   g.num_kb = (K + BK - 1) / BK;
-  g.last_kb_steps = (K - (g.num_kb - 1) * BK + 15) / 16;
   return run(tmA, B, ldb, M, N, K, g, epi, stream, nullptr, rows_per_group);
 }
 
@@ -1176,7 +1163,6 @@ int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* 
   g.Nimg = c.Nimg;
   g.HoWo = c.Ho * c.Wo;
   g.num_kb = c.ksize * c.ksize * g.cblocks;
-  g.last_kb_steps = (c.C - (g.cblocks - 1) * BK + 15) / 16;
   const long long M = (long long)c.Nimg * c.Ho * c.Wo;
   VIP_REQUIRE(M < (1LL << 31), VIP_ERR_UNSUPPORTED, "conv2d_bf16: too many output pixels");
   const int K = c.ksize * c.ksize * c.C;
