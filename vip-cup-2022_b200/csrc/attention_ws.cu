@@ -23,6 +23,9 @@
 
 #include "common.cuh"
 
+#ifndef VIP_ATTN_WS7_STAGES
+#define VIP_ATTN_WS7_STAGES 4   // measured at 56x56, batch 1024: 3 stages 317 us, 4 stages 303 us
+#endif
 #ifndef VIP_ATTN_POLY
 #define VIP_ATTN_POLY 1   // measured on B200 (ws 14, batch 1024): 0 -> 218 us, 1 -> 192, 2 -> 199, 3 -> 220
 #endif
@@ -186,7 +189,7 @@ struct WsCfg {
   static constexpr int TAB = (2 * WS - 1) * (2 * WS - 1);
   static constexpr int kQBytes = MT * 128 * 128, kKBytes = KEYS * 128;
   static constexpr int kStageBytes = kQBytes + 2 * kKBytes;   // q, k, v (multiples of 1024)
-  static constexpr int kStages = WS <= 8 ? 3 : 2;
+  static constexpr int kStages = WS <= 8 ? VIP_ATTN_WS7_STAGES : 2;
   static constexpr int kBoxBytes = N * 128;
   // TMEM columns of one softmax group
   static constexpr int S_COL = 0;
