@@ -88,18 +88,18 @@ def main():
             kw = {}
             byts = 2.0 * (m * k + m * n + n * k)
             if "ln" in ex.split():
-                kw.update(ln_stats=torch.rand(m, 2, device=dev) + torch.tensor([0.0, 70.0], device=dev), ln_colsum=torch.randn(n, device=dev),
+                kw.update(ln_stats=torch.tensor([0, 70 << 28, 0], dtype=torch.int64, device=dev).repeat(m, 1), ln_colsum=torch.randn(n, device=dev),
                           ln_cols=k)
             if "gelu" in ex.split():
                 kw.update(act="gelu")
             if "relu" in ex.split():
                 kw.update(act="relu")
             if "res" in ex.split():
-                kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 2, device=dev))
+                kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 3, dtype=torch.int64, device=dev))
                 byts += 2.0 * m * n
             if ex.startswith("gap"):
                 hw = int(ex[3:])
-                kw.update(gap=torch.zeros(m // hw, n, device=dev), gap_rows=hw)
+                kw.update(gap=torch.zeros(m // hw, n, dtype=torch.int64, device=dev), gap_rows=hw)
             out = torch.empty((m, n), dtype=torch.float32 if ex == "sigf32" else torch.bfloat16, device=dev)
             if ex == "sigf32":
                 kw.update(act="sigmoid")

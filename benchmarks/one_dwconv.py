@@ -16,7 +16,7 @@ def main():
     dev = torch.device("cuda:0")
     x = (torch.randn(B, H, H, C, device=dev) * 0.5).to(torch.bfloat16)
     w = torch.randn(3, 3, C, device=dev) * 0.2
-    gap = torch.zeros(B, C, device=dev)
+    gap = torch.zeros(B, C, dtype=torch.int64, device=dev)
     for _ in range(2):
         nn.dwconv3x3(x, w, gelu=True, gap=gap)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -15,9 +15,9 @@ else:
     m, n, k = map(int, a[:3]); ex = a[3:]
     A, w, bias = rnd(m, k), rnd(n, k), torch.randn(n, device=dev)
     kw = {}
-    if "ln" in ex: kw.update(ln_stats=torch.rand(m, 2, device=dev) + torch.tensor([0.0, 70.0], device=dev), ln_colsum=torch.randn(n, device=dev), ln_cols=k)
+    if "ln" in ex: kw.update(ln_stats=torch.tensor([0, 70 << 28, 0], dtype=torch.int64, device=dev).repeat(m, 1), ln_colsum=torch.randn(n, device=dev), ln_cols=k)
     if "gelu" in ex: kw.update(act="gelu")
-    if "res" in ex: kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 2, device=dev))
+    if "res" in ex: kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 3, dtype=torch.int64, device=dev))
     out = torch.empty((m, n), dtype=torch.bfloat16, device=dev)
     fn = lambda: nn.gemm(A, w, bias=bias, out=out, **kw)
 for _ in range(3): fn()

@@ -84,7 +84,7 @@ int vip_preprocess_host(const uint8_t* src, int N, int Hs, int Ws, const int32_t
  *   out[M,N] = act(A[M,K] x B[N,K]^T + bias[N]) * colscale[N] + residual[M,N]
  * A, B, residual: device bf16, row-major (lda / ldb / ldr elements between rows, multiples of 8); bias, colscale
  * (GCViT layer-scale gamma, models/gcvit/layers/block.py:41-56,79-80): device f32 or NULL; act: 0 none, 1 relu,
- * 2 gelu (erf), 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).  K % 8 == 0, N % 8 == 0. */
+ * 2 gelu, 3 sigmoid; out: device bf16 or f32 per out_dtype (ldc multiple of 8).  K % 8 == 0, N % 8 == 0. */
 int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
                   const float* colscale, const void* residual, int ldr, void* out, int ldc, int out_dtype,
                   void* cuda_stream);
@@ -92,33 +92,45 @@ int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, 
 /* Epilogue description of vip_gemm_bf16_ex / vip_conv2d_bf16, applied per output element (m, n) in this order:
  *   v = acc
  *   v = rstd[m] * (v - mean[m] * ln_colsum[n])   if ln_stats: LayerNormalization of the A rows folded into the contraction
- *        (models/gcvit/layers/block.py:28,39 feeding attention.py:25 / feature.py:20): (mean, rstd) come from ln_stats[m] =
- *        (sum, sum of squares) over ln_cols columns; B must hold gamma-scaled weights, bias must hold beta @ W + b
+ *        (models/gcvit/layers/block.py:28,39 feeding attention.py:25 / feature.py:20): (mean, rstd) come from the row
+ *        statistics record ln_stats[m] over ln_cols columns; B must hold gamma-scaled weights, bias must hold beta @ W + b
  *   v += bias[n];  v = act(v);  v *= colscale[n];  v += residual[m, n];  store as bf16 or f32
- *   row_stats[m] += (sum_n out, sum_n out^2)      if row_stats: feeds the ln_stats of the next contraction (f32 atomics)
+ *   row_stats[m] += (sum_n (out - p), sum_n (out - p)^2, p)   if row_stats: a row statistics record (below) that feeds the
+ *        ln_stats of the next contraction
  *   gap[m / gap_rows, n] += out                   if gap: GlobalAveragePooling2D partial sums (SE squeeze,
- *        models/resnet_rs/resnet_rs_model.py:149) (f32 atomics)
+ *        models/resnet_rs/resnet_rs_model.py:149), 36.28 fixed point
+ * Statistics that cross kernels are accumulated with 64-bit INTEGER atomics on fixed-point values (value * 2^28), so the
+ * totals do not depend on the order in which tiles finish: outputs are bit-reproducible and independent of the batch an
+ * image is in.  A row statistics record is int64[3] = { sum (v - p), sum (v - p)^2 (both fixed point), bits of the f32
+ * pivot p }; p is the row's previous column-0 value (0 without a residual), which keeps the one-pass variance free of
+ * cancellation when |mean| >> sigma.
+ * Two-plane residual stream (residual_lo / out_lo, both bf16 with the leading dimensions of residual / out): the running
+ * sum x of a pre-LN transformer block (models/gcvit/layers/block.py:77-81) is carried as hi + lo; v = acc + bias + hi + lo,
+ * out = bf16(v), out_lo = bf16(v - out).  The hi plane is the A operand of the next contraction; needs a residual, a bf16
+ * output and a bias-only epilogue.  residual_lo may be NULL (zeros) with out_lo set.
  * With row_gate the order is that of an SE bottleneck tail (resnet_rs_model.py:183,278-280):
  *   v = relu((acc + bias[n]) * row_gate[m / gate_rows, n] + residual[m, n])   (needs residual, act relu, bf16 output)
  * row_stats and gap are accumulated: the caller zeroes them (vip_memset_async). */
 typedef struct vip_epilogue {
   const float* bias;      /* [N] or NULL */
-  int act;                /* 0 none, 1 relu, 2 gelu (erf), 3 sigmoid */
+  int act;                /* 0 none, 1 relu, 2 gelu (Keras' erf form evaluated as a fitted tanh: |err| <= 3e-4 |x|), 3 sigmoid */
   const float* colscale;  /* [N] or NULL */
   const void* residual;   /* bf16 [M, ldr] or NULL */
   int ldr;
   void* out;              /* bf16 or f32 [M, ldc] */
   int ldc;
   int out_dtype;          /* VIP_DTYPE_* */
-  const float* ln_stats;  /* [M, 2] or NULL */
+  const int64_t* ln_stats; /* [M, 3] row statistics records or NULL */
   const float* ln_colsum; /* [N] */
   int ln_cols;
   float ln_eps;
-  float* row_stats;       /* [M, 2] or NULL */
-  float* gap;             /* [ceil(M / gap_rows), N] or NULL */
+  int64_t* row_stats;     /* [M, 3] row statistics records or NULL */
+  int64_t* gap;           /* [ceil(M / gap_rows), N] fixed point or NULL */
   int gap_rows;
   const float* row_gate;  /* f32 [ceil(M / gate_rows), N] or NULL: squeeze-excite gate of the image a row belongs to */
   int gate_rows;
+  const void* residual_lo; /* bf16 [M, ldr] or NULL: low plane of the residual */
+  void* out_lo;            /* bf16 [M, ldc] or NULL: low plane of the output */
 } vip_epilogue_t;
 
 /* vip_gemm_bf16 with the full epilogue. N, K, lda, ldb, ldc, ldr multiples of 8. */
@@ -147,14 +159,14 @@ int vip_global_avgpool_bf16(const void* x, int N, int HW, int C, void* out_bf16,
 int vip_scale_add_act_bf16(const void* y, const float* gate, const void* shortcut, void* out, int N, int HW, int C, int act,
                            void* cuda_stream);
 /* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79.  row_stats
- * (f32 [M,2] or NULL) receives (sum, sum of squares) of every OUTPUT row, the ln_stats of a LayerNorm folded into the
- * next contraction. */
-int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats, long long M,
+ * (int64 [M,3] or NULL) receives the row statistics record (see vip_epilogue_t) of every OUTPUT row, the ln_stats of a
+ * LayerNorm folded into the next contraction. */
+int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, int64_t* row_stats, long long M,
                        int C, float eps, void* cuda_stream);
 /* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134.
- * gap (f32 [N,C] or NULL, zeroed by the caller) accumulates the per-image channel sums of the output: the SE squeeze
- * (GlobalAveragePooling, feature.py:55) without a second pass over the map. */
-int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, float* gap, int N, int H, int W, int C, int gelu,
+ * gap (int64 [N,C] fixed point or NULL, zeroed by the caller) accumulates the per-image channel sums of the output: the
+ * SE squeeze (GlobalAveragePooling, feature.py:55) without a second pass over the map. */
+int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap, int N, int H, int W, int C, int gelu,
                        void* cuda_stream);
 /* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
 int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
@@ -180,16 +192,18 @@ int vip_gemm_grouped_bf16(const void* A, int lda, const void* B, int ldb, int M,
 int vip_scale_weights_bf16(const void* w, int ldw, const float* gate, int G, int N, int K, void* out, void* cuda_stream);
 /* Fused pre-LN MLP of a GCViT block (models/gcvit/layers/block.py:39-56,77-81; layers/feature.py:8-43):
  *   out[m, :] = x[m, :] + W2 gelu(W1 LayerNorm(x[m, :]) + b1) + b2     with LayerNorm folded like vip_epilogue_t.ln_stats:
- *   ln_stats [M, 2] = (sum, sum of squares) of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,
+ *   ln_stats int64 [M, 3] = row statistics records of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,
  *   colsum1 [hidden] their column sums, bias1 [hidden] = beta W1 + b1; w2 bf16 [C, ldw2], bias2 [C] (layer scale folded).
- *   x, out bf16 [M, C] contiguous; row_stats [M, 2] (or NULL) receives (sum, sum of squares) of the rows of out.
+ *   x, out bf16 [M, C] contiguous; row_stats int64 [M, 3] (or NULL) receives the records of the rows of out; x_lo /
+ *   out_lo (bf16 [M, C] or NULL): low planes of the two-plane residual stream (see vip_epilogue_t).
  * The hidden activations stay in TMEM / shared memory.  Built for (C, hidden) = (96, 192) and (64, 192); any other shape
  * returns VIP_ERR_UNSUPPORTED and the caller issues two vip_gemm_bf16_ex calls instead. */
-int vip_mlp_fused_bf16(const void* x, long long M, int C, int hidden, const float* ln_stats, float ln_eps, const void* w1,
-                       int ldw1, const float* colsum1, const float* bias1, const void* w2, int ldw2, const float* bias2,
-                       void* out, float* row_stats, void* cuda_stream);
-/* out = bf16(x * scale): pooled sums of the fused gap epilogue -> means (SE squeeze, resnet_rs_model.py:149) */
-int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* cuda_stream);
+int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int hidden, const int64_t* ln_stats, float ln_eps,
+                       const void* w1, int ldw1, const float* colsum1, const float* bias1, const void* w2, int ldw2,
+                       const float* bias2, void* out, void* out_lo, int64_t* row_stats, void* cuda_stream);
+/* out = bf16(x * 2^-28 * scale): fixed-point pooled sums of the fused gap epilogue -> means (SE squeeze,
+ * resnet_rs_model.py:149) */
+int vip_scale_cast_fx_bf16(const int64_t* x, float scale, void* out, long long n, void* cuda_stream);
 
 /* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
  * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */

@@ -197,15 +197,22 @@ def param_count(W: dict, include_head: bool = True) -> int:
 
 
 def calibrate_head(W: dict, feat: np.ndarray, head_kernel: str = "predictions/kernel", head_bias: str = "predictions/bias",
-                   seed: int = 0, target_std: float = 1.5) -> dict:
+                   seed: int = 0, target_std: float = 1.5, direction: str = "random") -> dict:
     """Random-init backbones give almost image-independent logits ('random-init degeneracy').
     Re-draw the head so that logits are centred and spread (std ``target_std``) over the calibration features
     ``feat`` [n, C]: probabilities then fall on both sides of the 0.487 threshold and label agreement means something.
-    Returns a copy of ``W`` with the new head."""
+    ``direction``: "random" = a Gaussian read-out direction; "pca" = the direction along which the calibration features
+    vary most from image to image (what a trained head would pick up), i.e. the largest image-dependent signal relative
+    to the backbone's numerical noise.  Returns a copy of ``W`` with the new head."""
     rng = np.random.default_rng(seed)
     k = W[head_kernel].shape[1]
     mu = feat.mean(axis=0)
     d = rng.standard_normal((feat.shape[1], k)).astype(np.float64)
+    if direction == "pca":
+        _, _, vt = np.linalg.svd((feat - mu).astype(np.float64), full_matrices=False)
+        d[:, -1] = vt[0] * np.sqrt(feat.shape[1])          # class 1 (or the single sigmoid unit) reads the first component
+        if k > 1:
+            d[:, :-1] *= 0.0
     z = (feat - mu) @ d
     spread = (z[:, 0] - z[:, 1]).std() if k > 1 else z[:, 0].std()
     kern = d * (target_std / max(spread, 1e-12))

@@ -6,8 +6,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant,head", [("tiny", "softmax"), ("small", "sigmoid"), ("xxtiny", "softmax")])
-def test_gcvit_matches_oracle(cuda_device, variant, head):
+@pytest.mark.parametrize("variant,head,seed", [("tiny", "softmax", 1), ("small", "sigmoid", 1), ("small", "softmax", 3),
+                                               ("xxtiny", "softmax", 5)])
+def test_gcvit_matches_oracle(cuda_device, variant, head, seed):
     import torch
 
     from oracle import gcvit as G
@@ -16,7 +17,7 @@ def test_gcvit_matches_oracle(cuda_device, variant, head):
     from vipcup_b200.models import GCViT
 
     k = 2 if head == "softmax" else 1
-    W = G.random_weights(variant, k, seed=5)
+    W = G.random_weights(variant, k, seed=seed)
     x = np.stack([P.decode_to_float(P.synth_image(i), 224, 224) for i in range(8)])
     ref_taps = {}
     ref = G.forward(x, W, variant, head_act=head, taps=ref_taps)
@@ -25,4 +26,4 @@ def test_gcvit_matches_oracle(cuda_device, variant, head):
     got = model(torch.from_numpy(x).to(cuda_device), taps=taps)
     torch.cuda.synchronize()
     check_against_oracle(ref, ref_taps, got, taps, W["head/kernel"], W["head/bias"],
-                         ("stem", "level0", "level1", "level2", "level3"), logit_tol=3e-2)
+                         ("stem", "level0", "level1", "level2", "level3"), logit_tol=1e-2)

@@ -3,6 +3,29 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+FX = 2.0 ** -28   # fixed-point unit of the cross-kernel accumulators (csrc/stats.cuh)
+
+
+def decode_stats(rec, cols):
+    """int64 [M, 3] row statistics records -> (mean, biased variance) per row, float64."""
+    import torch
+
+    piv = (rec[:, 2] & 0xFFFFFFFF).to(torch.int32).view(torch.float32).double()
+    d = rec[:, 0].double() * FX / cols
+    return piv + d, rec[:, 1].double() * FX / cols - d * d
+
+
+def encode_stats(x):
+    """Row statistics records of the rows of x (pivot = column 0), as a producer kernel would emit them."""
+    import torch
+
+    xf = x.double()
+    p = xf[:, :1]
+    s1 = torch.round((xf - p).sum(1) / FX).to(torch.int64)
+    s2 = torch.round(((xf - p) ** 2).sum(1) / FX).to(torch.int64)
+    pv = x[:, 0].float().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    return torch.stack([s1, s2, pv], 1).contiguous()
+
 
 @pytest.mark.parametrize("m,n,k", [
     (128, 32, 64), (128, 128, 64), (256, 256, 256), (1000, 64, 288), (625 * 3, 512, 1152), (49 * 5, 2048, 512),
@@ -52,12 +75,13 @@ def test_gemm_folded_layernorm_and_row_stats(cuda_device, m, n, k):
     a0 = (torch.randn(m, 64, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
     w0 = (torch.randn(k, 64, generator=g) * 0.3).to(torch.bfloat16).to(cuda_device)
     b0 = (torch.randn(k, generator=g) * 2.0).to(cuda_device)          # DC offset: mean removal must really happen
-    stats = nn.zero_(torch.empty((m, 2), dtype=torch.float32, device=cuda_device))
+    stats = nn.row_stats_buffer(m, device=cuda_device)
     x = nn.gemm(a0, w0, bias=b0, row_stats=stats)
     xs = x.float()
     torch.cuda.synchronize()
-    assert torch.allclose(stats[:, 0], xs.sum(1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[:, 1], (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+    mean, var = decode_stats(stats, k)
+    assert torch.allclose(mean, xs.double().mean(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(var, xs.double().var(1, unbiased=False), rtol=1e-4, atol=1e-5)
     # consumer: LN(x) * gamma + beta, then @ W + b, as one contraction on the raw x
     gamma = (1.0 + 0.2 * torch.randn(k, generator=g)).to(cuda_device)
     beta = (0.3 * torch.randn(k, generator=g)).to(cuda_device)
@@ -82,11 +106,15 @@ def test_gemm_fused_global_average_pool(cuda_device, nimg, hw, n, k):
     g = torch.Generator(device="cpu").manual_seed(nimg * hw + n)
     a = (torch.randn(nimg * hw, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
     b = (torch.randn(n, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
-    gap = nn.zero_(torch.empty((nimg, n), dtype=torch.float32, device=cuda_device))
+    gap = nn.zero_(torch.empty((nimg, n), dtype=torch.int64, device=cuda_device))
     out = nn.gemm(a, b, gap=gap, gap_rows=hw)
+    gap2 = nn.zero_(torch.empty((nimg, n), dtype=torch.int64, device=cuda_device))
+    out2 = nn.gemm(a, b, gap=gap2, gap_rows=hw)
     torch.cuda.synchronize()
-    ref = out.float().view(nimg, hw, n).sum(1)
-    assert torch.allclose(gap, ref, rtol=1e-3, atol=1e-2 * hw ** 0.5), (gap - ref).abs().max().item()
+    assert torch.equal(gap, gap2) and torch.equal(out, out2)      # integer atomics: order-independent, bit-reproducible
+    gap = gap.double() * FX
+    ref = out.double().view(nimg, hw, n).sum(1)
+    assert torch.allclose(gap, ref, rtol=1e-5, atol=1e-4 * hw ** 0.5), (gap - ref).abs().max().item()
     assert (out.float() - a.float() @ b.float().t()).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
 
 
@@ -120,13 +148,13 @@ def test_dwconv_fused_squeeze(cuda_device):
     g = torch.Generator(device="cpu").manual_seed(11)
     x = (torch.randn(3, 14, 14, 64, generator=g)).to(torch.bfloat16).to(cuda_device)
     w = (torch.randn(3, 3, 64, generator=g) * 0.3).to(cuda_device)
-    gap = nn.zero_(torch.empty((3, 64), dtype=torch.float32, device=cuda_device))
+    gap = nn.zero_(torch.empty((3, 64), dtype=torch.int64, device=cuda_device))
     y = nn.dwconv3x3(x, w, gelu=True, gap=gap)
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.permute(2, 0, 1)[:, None], padding=1, groups=64)
     ref = torch.nn.functional.gelu(ref).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
     assert (y.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
-    assert torch.allclose(gap, y.float().sum((1, 2)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(gap.double() * FX, y.double().sum((1, 2)), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("m,c", [(1000, 64), (4099, 96), (777, 128), (513, 192), (300, 384), (65, 768)])
@@ -142,15 +170,16 @@ def test_layernorm_matches_torch(cuda_device, m, c):
     x = (torch.randn((m, c), generator=g) * 2.0 + 0.5).to(torch.bfloat16).to(cuda_device)
     gamma = (torch.rand((c,), generator=g) + 0.5).to(cuda_device)
     beta = (torch.randn((c,), generator=g) * 0.3).to(cuda_device)
-    stats = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
+    stats = nn.row_stats_buffer(m, device=cuda_device)
     got = nn.layernorm(x, gamma, beta, eps=1e-5, row_stats=stats)
     ref = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
     torch.cuda.synchronize()
     err = (got.float() - ref).abs()
     assert (err <= ref.abs() * 2.0 ** -8 + 1e-3).all(), err.max().item()
-    gf = got.float()
-    assert torch.allclose(stats[:, 0], gf.sum(1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(stats[:, 1], (gf * gf).sum(1), rtol=1e-4, atol=1e-2)
+    gf = got.double()
+    mean, var = decode_stats(stats, c)
+    assert torch.allclose(mean, gf.mean(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(var, gf.var(1, unbiased=False), rtol=1e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("m,c,hidden", [(128, 96, 192), (1000, 96, 192), (40000, 96, 192), (777, 64, 192), (128 * 149 + 5, 64, 192)])
@@ -176,16 +205,23 @@ def test_mlp_fused_matches_two_gemms_and_torch(cuda_device, m, c, hidden):
     w2 = k2.T.contiguous().to(torch.bfloat16).to(cuda_device)               # [c, hidden]
     bias2 = b2.to(cuda_device)
     xf = x.float()
-    stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
-    rs_f = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
-    got = nn.mlp_fused(x, stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=rs_f)
+    stats = encode_stats(x)
+    x_lo = (torch.randn((m, c), generator=g) * 2.0 ** -9).to(torch.bfloat16).to(cuda_device)   # low plane of the stream
+    rs_f = nn.row_stats_buffer(m, device=cuda_device)
+    got, got_lo = nn.mlp_fused(x, stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=rs_f, x_lo=x_lo, want_lo=True)
     hdn = nn.gemm(x, w1, bias=bias1, act="gelu", ln_stats=stats, ln_colsum=colsum1, ln_cols=c, ln_eps=1e-5)
-    rs_g = torch.zeros((m, 2), dtype=torch.float32, device=cuda_device)
-    two = nn.gemm(hdn, w2, bias=bias2, residual=x, row_stats=rs_g)
+    rs_g = nn.row_stats_buffer(m, device=cuda_device)
+    two_lo = torch.empty_like(x)
+    two = nn.gemm(hdn, w2, bias=bias2, residual=x, row_stats=rs_g, residual_lo=x_lo, out_lo=two_lo)
     torch.cuda.synchronize()
     d = (got.float() - two.float()).abs()
     assert (d <= two.float().abs() * 2.0 ** -7 + 1e-3).all(), d.max().item()
-    assert torch.allclose(rs_f, rs_g, rtol=2e-3, atol=5e-2)
+    d2 = ((got.float() + got_lo.float()) - (two.float() + two_lo.float())).abs()     # the two-plane sums agree much closer
+    assert (d2 <= two.float().abs() * 2.0 ** -7 + 1e-3).all(), d2.max().item()
+    (mf, vf), (mg, vg) = decode_stats(rs_f, c), decode_stats(rs_g, c)
+    assert torch.allclose(mf, mg, rtol=2e-3, atol=2e-3) and torch.allclose(vf, vg, rtol=5e-3, atol=1e-3)
+    full = got.double() + got_lo.double()
+    assert torch.allclose(mf, full.mean(1), rtol=1e-4, atol=1e-4) and torch.allclose(vf, full.var(1, unbiased=False), rtol=1e-3, atol=1e-5)
     ln = torch.nn.functional.layer_norm(xf.cpu(), (c,), gamma, beta, 1e-5)
     ref = xf.cpu() + torch.nn.functional.gelu(ln @ k1 + b1) @ k2 + b2
     assert (got.float().cpu() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
@@ -212,3 +248,87 @@ def test_gemm_grouped_folds_a_per_image_input_scale(cuda_device, groups, rows, n
     ref = torch.einsum("gmk,gnk->gmn", y.float().view(groups, rows, k), wg.float().view(groups, n, k)).reshape(m, n) + res.float()
     err = (got.float() - ref).abs()
     assert (err <= ref.abs() * 2.0 ** -8 + 2e-3).all(), err.max().item()
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 64, 64), (4099, 96, 96), (1000, 384, 768), (777, 768, 1536), (128 * 150, 192, 192)])
+def test_gemm_two_plane_residual_stream(cuda_device, m, n, k):
+    """residual_lo / out_lo (vip_epilogue_t): the block residual stream of models/gcvit/layers/block.py:77-81 carried as
+    hi + lo bf16 planes.  hi + lo must reproduce acc + bias + (res_hi + res_lo) to ~2^-16 relative (a single bf16 plane
+    gives 2^-9), the row statistics must describe hi + lo, and two launches must agree bit for bit."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    g = torch.Generator(device="cpu").manual_seed(m + 3 * n + k)
+    a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(torch.bfloat16).to(cuda_device)
+    bias = torch.randn(n, generator=g).to(cuda_device)
+    res = (torch.randn(m, n, generator=g) * 3.0 + 5.0)
+    hi = res.to(torch.bfloat16)
+    lo = (res - hi.float()).to(torch.bfloat16)
+    hi, lo = hi.to(cuda_device), lo.to(cuda_device)
+    outs = []
+    for _ in range(2):
+        st = nn.row_stats_buffer(m, device=cuda_device)
+        out_lo = torch.empty((m, n), dtype=torch.bfloat16, device=cuda_device)
+        out = nn.gemm(a, w, bias=bias, residual=hi, residual_lo=lo, out_lo=out_lo, row_stats=st)
+        outs.append((out, out_lo, st))
+    torch.cuda.synchronize()
+    for t0, t1 in zip(*outs):
+        assert torch.equal(t0, t1)
+    out, out_lo, st = outs[0]
+    ref = a.double() @ w.double().t() + bias.double() + hi.double() + lo.double()
+    two = out.double() + out_lo.double()
+    err = (two - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -15 + 1e-5).all(), err.max().item()     # fp32 accumulation + 16-bit planes
+    one = (out.double() - ref).abs()
+    assert one.max() > 8 * err.max()                                          # the low plane really carries the remainder
+    mean, var = decode_stats(st, n)
+    assert torch.allclose(mean, ref.mean(1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(var, ref.var(1, unbiased=False), rtol=1e-4, atol=1e-5)
+    # first block of a level: no incoming low plane
+    out_lo2 = torch.empty_like(out_lo)
+    out2 = nn.gemm(a, w, bias=bias, residual=hi, out_lo=out_lo2)
+    ref2 = a.double() @ w.double().t() + bias.double() + hi.double()
+    torch.cuda.synchronize()
+    assert ((out2.double() + out_lo2.double() - ref2).abs() <= ref2.abs() * 2.0 ** -15 + 1e-5).all()
+
+
+@pytest.mark.parametrize("c,n", [(96, 288), (384, 768)])
+def test_folded_layernorm_with_large_row_mean(cuda_device, c, n):
+    """Rows with |mean| >> sigma (mean 50, sigma 0.1 -- outlier channels of trained ViT residual streams): the pivoted
+    one-pass statistics (csrc/stats.cuh) must not lose the variance to cancellation.  Producer = a two-plane residual GEMM,
+    consumer = a contraction with the LayerNorm folded in, reference = torch.nn.functional.layer_norm in float64."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    m = 1000
+    g = torch.Generator(device="cpu").manual_seed(c)
+    x0 = 50.0 + 0.1 * torch.randn(m, c, generator=g)
+    hi = x0.to(torch.bfloat16)
+    lo = (x0 - hi.float()).to(torch.bfloat16)
+    hi, lo = hi.to(cuda_device), lo.to(cuda_device)
+    a = (torch.randn(m, 64, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
+    w0 = (torch.randn(c, 64, generator=g) * 0.1).to(torch.bfloat16).to(cuda_device)
+    st = nn.row_stats_buffer(m, device=cuda_device)
+    x_lo = torch.empty((m, c), dtype=torch.bfloat16, device=cuda_device)
+    x = nn.gemm(a, w0, residual=hi, residual_lo=lo, out_lo=x_lo, row_stats=st)
+    torch.cuda.synchronize()
+    full = x.double() + x_lo.double()
+    mean, var = decode_stats(st, c)
+    assert torch.allclose(mean, full.mean(1), rtol=1e-6, atol=1e-5)
+    assert torch.allclose(var, full.var(1, unbiased=False), rtol=2e-3, atol=1e-7), (var - full.var(1, unbiased=False)).abs().max()
+    # the LayerNorm itself, through the folded contraction with identity-like weights: out = LN(x) @ W^T
+    gamma = (1.0 + 0.1 * torch.randn(c, generator=g)).to(cuda_device)
+    beta = (0.1 * torch.randn(c, generator=g)).to(cuda_device)
+    wt = (torch.randn(n, c, generator=g) / c ** 0.5).to(cuda_device)
+    wg = (wt * gamma[None, :]).to(torch.bfloat16)
+    out = nn.gemm(x, wg, bias=(wt @ beta).contiguous(), ln_stats=st, ln_colsum=wg.float().sum(1).contiguous(), ln_cols=c,
+                  ln_eps=1e-5, out_dtype=torch.float32)
+    # reference on the operand the kernel contracts (the hi plane) with the statistics of the full-precision stream
+    mu, sd = full.mean(1, keepdim=True), (full.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt()
+    ref = ((x.double() - mu) / sd) @ wg.double().t() + (wt.double() @ beta.double())
+    torch.cuda.synchronize()
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err

@@ -165,3 +165,37 @@ def test_host_buffer_entry_point(cuda_device):
                               torch.from_numpy(q).pin_memory(), torch.from_numpy(flags).pin_memory())
     ref = P.preprocess_batch(src, 224, 224, crops, q, flags)
     assert _bits_equal(out.numpy(), ref)
+
+
+@pytest.mark.parametrize("hs,ws,ho,wo,n", [
+    (200, 200, 224, 224, 40),   # GCViT path of main.py (streaming kernel, 14 stripes of 16 rows)
+    (200, 200, 200, 200, 40),   # ResNet-RS path: identity fast path for unflagged images, tap path for flagged ones
+    (180, 220, 200, 200, 5),    # other source sizes (dataset/dataset.py:33-34), down- and up-scale at once
+    (512, 512, 200, 200, 3),    # strong downscale: many source rows per stripe
+    (64, 64, 256, 256, 3),      # strong upscale: repeated taps, clamped borders
+    (8, 16, 8, 8, 7),           # tiny
+])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_streaming_kernel_parity_with_oracle(cuda_device, hs, ws, ho, wo, n, bf16):
+    """vip_preprocess without crop / JPEG emulation takes the streaming kernel (csrc/preprocess_stream.cu): bit-exact
+    against the oracle for every flag combination (flips as addressing, gray), both output types; bf16 = RN of the f32."""
+    import torch
+
+    from oracle import preprocess as P
+
+    rng = np.random.default_rng(hs + 3 * ws + ho)
+    src = np.stack([P.synth_image(i, hs, ws) if i % 3 else rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+                    for i in range(n)])
+    flags = (np.arange(n) % 8).astype(np.uint8)
+    ref = P.preprocess_batch(src, ho, wo, None, None, flags)
+    got = _run(cuda_device, src, (ho, wo), None, None, flags, dtype=torch.bfloat16 if bf16 else torch.float32)
+    if bf16:
+        assert torch.equal(got.cpu(), torch.from_numpy(ref).to(torch.bfloat16))
+    else:
+        bad = np.argwhere(got.cpu().numpy().view(np.uint32) != ref.view(np.uint32))
+        assert bad.size == 0, f"{len(bad)} mismatching elements, first at {bad[0]}"
+    # the streaming and the fused kernel agree: q = -1 everywhere forces the fused (JPEG-capable) kernel
+    fused = _run(cuda_device, src, (ho, wo), None, np.full(n, -1, np.int32), flags, dtype=torch.bfloat16 if bf16 else torch.float32)
+    assert torch.equal(got, fused)
+    none = _run(cuda_device, src, (ho, wo), None, None, None, dtype=torch.bfloat16 if bf16 else torch.float32)
+    assert torch.equal(none[::8], got[::8])     # flags == 0 images: same result with and without a flags array

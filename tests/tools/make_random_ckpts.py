@@ -24,9 +24,10 @@ def weights_for(model_name, num_classes, seed):
 
 
 def centred(model_name, W, n_cal=16):
-    """Random-init backbones are almost image-independent: re-draw the head so that the logit
-    margin has std 2 over the synthetic images and its median sits on the 0.487 threshold.  This amplifies the
-    backbone's bf16 error by the same factor as the signal, so labels are only comparable away from the threshold."""
+    """Random-init backbones are almost image-independent: re-draw the head along the first
+    principal component of the calibration features so that the logit margin has std 2 over the synthetic images and its
+    median sits on the 0.487 threshold.  The read-out amplifies the backbone's bf16 error by the same factor as the
+    signal, so tests select images whose oracle margin exceeds the measured error (make_decided_dataset.py)."""
     from oracle import gcvit as G
     from oracle import preprocess as P
     from oracle import resnet_rs as R
@@ -37,10 +38,10 @@ def centred(model_name, W, n_cal=16):
     taps = {}
     if arch.startswith("ResNetRS"):
         R.forward(x, W, int(arch[len("ResNetRS"):]), taps=taps)
-        W = R.calibrate_head(W, taps["feat"], seed=1, target_std=2.0)
+        W = R.calibrate_head(W, taps["feat"], seed=1, target_std=2.0, direction="pca")
         return R.center_head(W, taps["feat"])
     G.forward(x, W, arch[len("GCViT"):].lower(), taps=taps)
-    W = R.calibrate_head(W, taps["feat"], "head/kernel", "head/bias", seed=1, target_std=2.0)
+    W = R.calibrate_head(W, taps["feat"], "head/kernel", "head/bias", seed=1, target_std=2.0, direction="pca")
     return R.center_head(W, taps["feat"], head_kernel="head/kernel", head_bias="head/bias")
 
 

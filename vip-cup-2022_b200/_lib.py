@@ -21,7 +21,7 @@ class Epilogue(C.Structure):
                 ("ldr", C.c_int), ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
                 ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
                 ("row_stats", C.c_void_p), ("gap", C.c_void_p), ("gap_rows", C.c_int),
-                ("row_gate", C.c_void_p), ("gate_rows", C.c_int)]
+                ("row_gate", C.c_void_p), ("gate_rows", C.c_int), ("residual_lo", C.c_void_p), ("out_lo", C.c_void_p)]
 
 
 _lib = None
@@ -55,12 +55,13 @@ SIGNATURES = {
     "vip_window_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "vip_head_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
-    "vip_scale_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "vip_scale_cast_fx_bf16": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vip_gemm_grouped_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.POINTER(Epilogue), C.c_void_p]),
     "vip_scale_weights_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "vip_mlp_fused_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vip_mlp_fused_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "vip_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vip_selftest_div255": (C.c_int, [C.POINTER(C.c_uint64), C.c_void_p]),
 }

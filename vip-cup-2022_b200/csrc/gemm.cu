@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "gemm.cuh"
+#include "stats.cuh"
 
 namespace vip {
 namespace {
@@ -311,7 +312,9 @@ template <int MODE>
 __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
                                           int N, float rstd, float nmr, const float* __restrict__ colsum,
                                           const float* __restrict__ bias, float& rs_sum, float& rs_sq,
-                                          const float* __restrict__ gate_row = nullptr) {
+                                          const float* __restrict__ gate_row = nullptr, float pivot = 0.0f,
+                                          const __nv_bfloat16* __restrict__ lo_in = nullptr,
+                                          __nv_bfloat16* __restrict__ lo_out = nullptr) {
   constexpr bool kLN = MODE == EPI_LN || MODE == EPI_LN_GELU;
   constexpr bool kGelu = MODE == EPI_GELU || MODE == EPI_LN_GELU;
 #pragma unroll
@@ -356,10 +359,20 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
         v[2 * t] += __uint_as_float(w[t] << 16);
         v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
       }
+      if (lo_in != nullptr) {   // low plane of the two-plane residual stream (null for rows beyond M)
+        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo_in + n));
+        const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          v[2 * t] += __uint_as_float(wl[t] << 16);
+          v[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        rs_sum += v[i];
-        rs_sq = fmaf(v[i], v[i], rs_sq);
+        const float d = v[i] - pivot;
+        rs_sum += d;
+        rs_sq = fmaf(d, d, rs_sq);
       }
     }
     uint32_t w[4];
@@ -369,6 +382,16 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
       w[t] = *reinterpret_cast<const uint32_t*>(&h2);
     }
     *cp = make_uint4(w[0], w[1], w[2], w[3]);
+    if (MODE == EPI_RES && lo_out != nullptr) {   // what the bf16 rounding of the high plane dropped
+      uint32_t wl[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * t] - __uint_as_float(w[t] << 16),
+                                                        v[2 * t + 1] - __uint_as_float(w[t] & 0xffff0000u));
+        wl[t] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      *reinterpret_cast<uint4*>(lo_out + n) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
   }
 }
 
@@ -377,7 +400,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
                                               int N, int row, int M, const GemmEpilogue& e, bool has_res, float rstd,
                                               float nmr, const float* __restrict__ p_colsum,
                                               const float* __restrict__ p_bias, const float* __restrict__ p_colscale,
-                                              float& rs_sum, float& rs_sq) {
+                                              float& rs_sum, float& rs_sq, float pivot) {
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
     const int n = nb + q8 * 8;
@@ -407,7 +430,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
       for (int t = 0; t < 4; ++t) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
         w[t] = *reinterpret_cast<const uint32_t*>(&h2);
-        const float lo = __uint_as_float(w[t] << 16), hi = __uint_as_float(w[t] & 0xffff0000u);
+        const float lo = __uint_as_float(w[t] << 16) - pivot, hi = __uint_as_float(w[t] & 0xffff0000u) - pivot;
         rs_sum += lo + hi;
         rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
       }
@@ -638,12 +661,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
     uint32_t tcount = 0;  // tiles processed by this CTA; tile t stages into buffer set t % kSets
     // row statistics of the folded LayerNorm: fetched one tile ahead so that the load never sits on the critical path
-    auto load_stats = [&](int tile_) -> float2 {
+    struct StatRec { long long s1, s2, pv; };
+    auto load_stats = [&](int tile_) -> StatRec {
       const long long row_ = ((long long)(tile_ / g.n_tiles) * kCtas + cta_rank) * BM + rt;
-      if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return make_float2(0.0f, 0.0f);
-      return __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row_);
+      if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return StatRec{0, 0, 0};
+      const long long* rec = e.ln_stats + 3 * row_;
+      return StatRec{__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
     };
-    float2 st_next = load_stats(cta_tile0);
+    StatRec st_next = load_stats(cta_tile0);
     for (int tile = cta_tile0; tile < total_tiles; tile += cta_tile_step, ++tcount) {
       const int m0 = ((tile / g.n_tiles) * kCtas + (int)cta_rank) * BM, n0 = (tile % g.n_tiles) * BN;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -660,12 +685,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       float rstd = 1.0f, nmr = 0.0f;  // 1/sigma and -mean/sigma of this row (identity without a folded LayerNorm)
       if (e.ln_stats != nullptr) {
-        const float2 st = st_next;
+        const StatRec st = st_next;
         st_next = load_stats(tile + cta_tile_step);
-        const float inv = 1.0f / (float)e.ln_cols;
-        const float mean = st.x * inv;
-        rstd = rsqrtf(fmaxf(st.y * inv - mean * mean, 0.0f) + e.ln_eps);
-        nmr = -mean * rstd;
+        const RowMoments mo = row_moments(st.s1, st.s2, st.pv, 1.0f / (float)e.ln_cols, e.ln_eps);
+        rstd = mo.rstd;
+        nmr = -mo.mean * mo.rstd;
+      }
+      // two-plane residual stream: this row's low planes; pivot of the row statistics = the row's previous value of
+      // column 0 (every thread of the row fetches the same two numbers, whichever N tile it works on)
+      const bool row_ok = row < g.M;
+      const __nv_bfloat16* lo_in = (e.residual_lo != nullptr && row_ok) ? e.residual_lo + (size_t)row * e.ldr : nullptr;
+      __nv_bfloat16* lo_out = (e.out_lo != nullptr && row_ok) ? e.out_lo + (size_t)row * e.ldc : nullptr;
+      float pivot = 0.0f;
+      if (e.row_stats != nullptr && has_res && row_ok) {
+        pivot = __bfloat162float(e.residual[(size_t)row * e.ldr]);
+        if (lo_in != nullptr) pivot += __bfloat162float(lo_in[0]);
       }
       const float* gate_row = e.row_gate != nullptr ? e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N : nullptr;
       if (kPair) mbar_wait_spin(&tfull_bar[as], aph);
@@ -736,9 +770,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
             case EPI_SE: epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq, gate_row); break;
-            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
+            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq, nullptr, pivot, lo_in, lo_out); break;
             default:
-              epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, rs_sum, rs_sq);
+              epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, rs_sum, rs_sq, pivot);
               break;
           }
         }
@@ -782,8 +816,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (pn0 + ni >= g.Nimg || pp0 + py >= g.Ho || pq0 + px >= g.Wo) continue;
               if (ni != cur) {
                 if (cur >= 0) {
-                  atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
-                  atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+                  fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+                  fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
                 }
                 s0 = s1 = 0.0f;
                 cur = ni;
@@ -794,8 +828,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               s1 += __uint_as_float(w & 0xffff0000u);
             }
             if (cur >= 0) {
-              atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
-              atomicAdd(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+              fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+              fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
             }
           } else if (m0 + rq * kGapRows < g.M) {
             int rr = rq * kGapRows;
@@ -804,8 +838,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < kGapRows; ++k, ++rr) {
               if (m0 + rr >= g.M) break;
               if (rr == next) {
-                atomicAdd(e.gap + (size_t)img * g.N + n, s0);
-                atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
+                fx_atomic_add(e.gap + (size_t)img * g.N + n, s0);
+                fx_atomic_add(e.gap + (size_t)img * g.N + n + 1, s1);
                 s0 = s1 = 0.0f;
                 ++img;
                 next += e.gap_rows;
@@ -815,15 +849,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               s0 += __uint_as_float(w << 16);
               s1 += __uint_as_float(w & 0xffff0000u);
             }
-            atomicAdd(e.gap + (size_t)img * g.N + n, s0);
-            atomicAdd(e.gap + (size_t)img * g.N + n + 1, s1);
+            fx_atomic_add(e.gap + (size_t)img * g.N + n, s0);
+            fx_atomic_add(e.gap + (size_t)img * g.N + n + 1, s1);
           }
         }
       }
       if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 6] = clock64();
       if (e.row_stats != nullptr && row < g.M && j_last >= j_first) {
-        atomicAdd(e.row_stats + 2 * (size_t)row, rs_sum);
-        atomicAdd(e.row_stats + 2 * (size_t)row + 1, rs_sq);
+        long long* rec = e.row_stats + 3 * (size_t)row;
+        fx_atomic_add(rec, rs_sum);
+        fx_atomic_add(rec + 1, rs_sq);
+        if (n0 == 0 && group == 0) rec[2] = (long long)__float_as_int(pivot);   // the thread that holds column 0
       }
     }
     if (storer) tma_store_wait_all();
@@ -1013,6 +1049,13 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
   VIP_REQUIRE((epi.row_stats == nullptr && epi.gap == nullptr) || epi.out_bf16 != nullptr, VIP_ERR_UNSUPPORTED,
               "gemm: row_stats / gap need a bf16 output");
   VIP_REQUIRE(epi.gap == nullptr || epi.gap_rows > 0, VIP_ERR_INVALID, "gemm: gap_rows must be set with gap");
+  VIP_REQUIRE(epi.gap == nullptr || epi.residual == nullptr, VIP_ERR_UNSUPPORTED,
+              "gemm: gap with a residual is not supported (the pooled sums read the staging buffers the next residual tile lands in)");
+  VIP_REQUIRE((epi.residual_lo == nullptr && epi.out_lo == nullptr) ||
+                  (epi.residual != nullptr && epi.out_bf16 != nullptr && epi.act == ACT_NONE && epi.ln_stats == nullptr &&
+                   epi.colscale == nullptr && epi.row_gate == nullptr),
+              VIP_ERR_UNSUPPORTED, "gemm: residual_lo / out_lo need a residual, a bf16 output and a plain (bias only) epilogue");
+  VIP_REQUIRE((((uintptr_t)epi.residual_lo | (uintptr_t)epi.out_lo) & 15) == 0, VIP_ERR_INVALID, "gemm: unaligned low plane");
   VIP_REQUIRE(epi.row_gate == nullptr ||
                   (epi.gate_rows > 0 && epi.residual != nullptr && epi.act == ACT_RELU && epi.out_bf16 != nullptr &&
                    epi.ln_stats == nullptr && epi.colscale == nullptr && epi.row_stats == nullptr),
@@ -1243,12 +1286,14 @@ vip::GemmEpilogue to_epilogue(const vip_epilogue_t* p) {
   e.ldc = p->ldc;
   if (p->out_dtype == VIP_DTYPE_BF16) e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out);
   else e.out_f32 = reinterpret_cast<float*>(p->out);
-  e.ln_stats = p->ln_stats;
+  e.ln_stats = reinterpret_cast<const long long*>(p->ln_stats);
   e.ln_colsum = p->ln_colsum;
   e.ln_cols = p->ln_cols;
   e.ln_eps = p->ln_eps;
-  e.row_stats = p->row_stats;
-  e.gap = p->gap;
+  e.row_stats = reinterpret_cast<long long*>(p->row_stats);
+  e.gap = reinterpret_cast<long long*>(p->gap);
+  e.residual_lo = reinterpret_cast<const __nv_bfloat16*>(p->residual_lo);
+  e.out_lo = reinterpret_cast<__nv_bfloat16*>(p->out_lo);
   e.gap_rows = p->gap_rows;
   e.row_gate = p->row_gate;
   e.gate_rows = p->gate_rows;

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "stats.cuh"
 
 namespace vip {
 namespace {
@@ -239,7 +240,7 @@ __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __
 template <int LPR, int J, int U>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        float* __restrict__ row_stats, long long M, int C, float eps) {
+                                                        long long* __restrict__ row_stats, long long M, int C, float eps) {
   pdl_trigger();
   pdl_wait();
   constexpr int RPW = 32 / LPR;  // rows per warp and group
@@ -290,8 +291,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
       }
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      const float rstd = rsqrtf(v * invC + eps);
-      float os = 0.0f, oq = 0.0f;  // statistics of the rounded output row (for a LayerNorm folded into the next GEMM)
+      const float rstd = 1.0f / sqrtf(v * invC + eps);
+      // statistics record of the rounded output row (for a LayerNorm folded into the next GEMM), shifted by the row's
+      // first output element (stats.cuh)
+      float os = 0.0f, oq = 0.0f, pivot = 0.0f;
+      if (row_stats != nullptr) {
+        const float g0 = __ldg(gamma), b0 = __ldg(beta);
+        const float first = __bfloat162float(__float2bfloat16_rn(fmaf((f[u][0][0] - mean) * rstd, g0, b0)));  // valid in lane sub == 0
+        pivot = __shfl_sync(0xffffffffu, first, rsel * LPR);
+      }
 #pragma unroll
       for (int j = 0; j < J; ++j) {
         const int c8 = sub + LPR * j;
@@ -310,8 +318,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
             unpack8(pk, r8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              os += r8[k];
-              oq = fmaf(r8[k], r8[k], oq);
+              const float d = r8[k] - pivot;
+              os += d;
+              oq = fmaf(d, d, oq);
             }
           }
         }
@@ -322,7 +331,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
           os += __shfl_xor_sync(0xffffffffu, os, o);
           oq += __shfl_xor_sync(0xffffffffu, oq, o);
         }
-        if (sub == 0 && live) *reinterpret_cast<float2*>(row_stats + 2 * m) = make_float2(os, oq);
+        if (sub == 0 && live) {
+          long long* rec = row_stats + 3 * m;
+          rec[0] = to_fx(os);
+          rec[1] = to_fx(oq);
+          rec[2] = (long long)__float_as_int(pivot);
+        }
       }
     }
   }
@@ -379,7 +393,7 @@ __device__ __forceinline__ float2 bf16pair(uint32_t w) {  // two bf16 -> two fp3
 // rows ahead as cp.async into thread-private shared-memory slots (no block barrier, no register cost).
 template <int P, int D, int MINB>  // channel pairs per thread: 4 (16-byte accesses) or 2 (8-byte); prefetch depth in rows
 __global__ void __launch_bounds__(128, MINB) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[3][3][C]*/,
-                                                        bf16* __restrict__ out, float* __restrict__ gap /*[N][C] or null*/,
+                                                        bf16* __restrict__ out, long long* __restrict__ gap /*[N][C] fixed point or null*/,
                                                         int N, int H, int W, int C, int gelu) {
   pdl_trigger();
   pdl_wait();
@@ -480,8 +494,8 @@ __global__ void __launch_bounds__(128, MINB) dwconv3x3_kernel(const bf16* __rest
   if (gap != nullptr && active) {
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-      atomicAdd(gap + (long long)n * C + cv * V + 2 * q, colsum[q].x);
-      atomicAdd(gap + (long long)n * C + cv * V + 2 * q + 1, colsum[q].y);
+      fx_atomic_add(gap + (long long)n * C + cv * V + 2 * q, colsum[q].x);
+      fx_atomic_add(gap + (long long)n * C + cv * V + 2 * q + 1, colsum[q].y);
     }
   }
 }
@@ -572,11 +586,11 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
 }
 
 // ---- out = bf16(x * scale): pooled sums -> means as a GEMM operand (SE squeeze, resnet_rs_model.py:149)
-__global__ void scale_cast_f32_bf16_kernel(const float* __restrict__ x, float scale, bf16* __restrict__ out, long long n) {
+__global__ void scale_cast_fx_bf16_kernel(const long long* __restrict__ x, float scale, bf16* __restrict__ out, long long n) {
   pdl_trigger();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(x[i] * scale);
+    out[i] = __float2bfloat16_rn(from_fx(x[i]) * scale);
 }
 
 // ---- out[g][n][k] = bf16(w[n][k] * gate[g][k]): the SE gate of an MBConv block (feature.py:49-66,144-150) scales the INPUT
@@ -647,8 +661,9 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats,
+extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, int64_t* row_stats_,
                                   long long M, int C, float eps, void* stream) {
+  long long* row_stats = reinterpret_cast<long long*>(row_stats_);
   VIP_REQUIRE(x && out && gamma && beta && C % 8 == 0 && C <= 1024, VIP_ERR_INVALID,
               "vip_layernorm_bf16: bad argument (C %% 8 == 0, C <= 1024)");
   const bf16* xp = (const bf16*)x;
@@ -666,8 +681,9 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, float* gap, int N, int H, int W, int C, int gelu,
+extern "C" int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap_, int N, int H, int W, int C, int gelu,
                                   void* stream) {
+  long long* gap = reinterpret_cast<long long*>(gap_);
   VIP_REQUIRE(x && out && w && C % 8 == 0, VIP_ERR_INVALID, "vip_dwconv3x3_bf16: bad argument");
   // measured at [1024, 100, 100, 96] on B200: 8 channels per thread, 4 rows ahead, 3 blocks per SM (168 registers) 1.59 ms;
   // 2 blocks (202 registers) 1.61; depth 2 / 6 the same; 4 channels per thread 1.73; the register-window version 2.21
@@ -690,9 +706,9 @@ extern "C" int vip_head_f32(const float* feat, const float* w, const float* b, f
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_scale_cast_f32_bf16(const float* x, float scale, void* out, long long n, void* stream) {
-  VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_f32_bf16: null pointer");
-  VIP_LAUNCH((scale_cast_f32_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), x, scale, (bf16*)out, n);
+extern "C" int vip_scale_cast_fx_bf16(const int64_t* x, float scale, void* out, long long n, void* stream) {
+  VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_fx_bf16: null pointer");
+  VIP_LAUNCH((scale_cast_fx_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), reinterpret_cast<const long long*>(x), scale, (bf16*)out, n);
   LAUNCH_CHECK();
 }
 

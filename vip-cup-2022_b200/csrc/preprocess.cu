@@ -20,8 +20,10 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "resize_math.cuh"
 
 namespace vip {
 namespace {
@@ -54,66 +56,6 @@ __constant__ uint8_t c_chroma_base[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21
                                           24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
                                           99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
                                           99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
-
-// ---- exact helpers --------------------------------------------------------------------------------------
-// x / 255.0f, correctly rounded, for every finite x with 1e-30 <= |x| <= 1e30 and +0 (Markstein: RN(1/255)
-// multiply, exact remainder by FMA, one correction).  Exhaustively verified on the CPU and by
-// vip_selftest_div255 on the device.
-__device__ __forceinline__ float div255(float x) {
-  const float rc = 0.003921568859368562698f;
-  const float q0 = __fmul_rn(x, rc);
-  const float r = __fmaf_rn(-q0, 255.0f, x);
-  return __fmaf_rn(r, rc, q0);
-}
-
-// Keys cubic (a = -0.5) LUT entry exactly as TF's InitCoeffsTable: double arithmetic on a float abscissa,
-// rounded to float once.  i in [0, 1024].
-__device__ float coeff_near(int i) {
-  const double x = (double)((float)i * 0.0009765625f);
-  double t = __dadd_rn(__dmul_rn(1.5, x), -2.5);
-  t = __dmul_rn(__dmul_rn(t, x), x);
-  return __double2float_rn(__dadd_rn(t, 1.0));
-}
-__device__ float coeff_far(int i) {
-  const double x = (double)((float)i * 0.0009765625f + 1.0f);
-  double t = __dadd_rn(__dmul_rn(-0.5, x), 2.5);
-  t = __dadd_rn(__dmul_rn(t, x), -4.0);
-  t = __dmul_rn(t, x);
-  return __double2float_rn(__dadd_rn(t, 2.0));
-}
-
-// TF GetWeightsAndIndices<HalfPixelScaler, use_keys_cubic=true>
-__device__ void compute_tap(int o, int in_size, int out_size, float4* w_out, short4* i_out) {
-  const float scale = __fdiv_rn((float)in_size, (float)out_size);
-  const float loc = __fsub_rn(__fmul_rn(__fadd_rn((float)o, 0.5f), scale), 0.5f);
-  const float fl = floorf(loc);
-  const int il = (int)fl;
-  const float delta = __fsub_rn(loc, fl);
-  const int off = __float2int_rn(__fmul_rn(delta, 1024.0f));
-  const int lim = in_size - 1;
-  const int r0 = il - 1, r1 = il, r2 = il + 1, r3 = il + 2;
-  const int i0 = min(max(r0, 0), lim), i1 = min(max(r1, 0), lim);
-  const int i2 = min(max(r2, 0), lim), i3 = min(max(r3, 0), lim);
-  float w0 = (i0 == r0) ? coeff_far(off) : 0.0f;
-  float w1 = (i1 == r1) ? coeff_near(off) : 0.0f;
-  float w2 = (i2 == r2) ? coeff_near(1024 - off) : 0.0f;
-  float w3 = (i3 == r3) ? coeff_far(1024 - off) : 0.0f;
-  const float sum = __fadd_rn(__fadd_rn(__fadd_rn(w0, w1), w2), w3);
-  if (fabsf(sum) >= 1000.0f * 1.17549435e-38f) {
-    const float inv = __fdiv_rn(1.0f, sum);
-    w0 = __fmul_rn(w0, inv);
-    w1 = __fmul_rn(w1, inv);
-    w2 = __fmul_rn(w2, inv);
-    w3 = __fmul_rn(w3, inv);
-  }
-  *w_out = make_float4(w0, w1, w2, w3);
-  *i_out = make_short4((short)i0, (short)i1, (short)i2, (short)i3);
-}
-
-__device__ __forceinline__ float tap4(float p0, float p1, float p2, float p3, const float4 w) {
-  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(p0, w.x), __fmul_rn(p1, w.y)), __fmul_rn(p2, w.z)),
-                   __fmul_rn(p3, w.w));
-}
 
 // ---- libjpeg islow DCTs (jfdctint.c / jidctint.c), one 8-vector per call -----------------------------
 #define C0298 2446
@@ -237,13 +179,6 @@ __device__ __forceinline__ void store_px(void* img, size_t img_elem0, int Wo, in
   }
 }
 
-__device__ __forceinline__ void gray3(float* p) {
-  const float g = __fadd_rn(__fadd_rn(__fmul_rn(p[0], 0.2989f), __fmul_rn(p[1], 0.5870f)), __fmul_rn(p[2], 0.1140f));
-  p[0] = g;
-  p[1] = g;
-  p[2] = g;
-}
-
 // Emits the 2x2 quad whose top-left real pixel is (2cy, 2cx); v[dy][dx][c] are final float values.
 template <bool kBf16>
 __device__ __forceinline__ void emit_quad(void* img, size_t e0, int Ho, int Wo, int cy, int cx, unsigned flags,
@@ -298,18 +233,6 @@ struct FastDiv {
   __device__ __forceinline__ explicit FastDiv(int d_) : m(0xffffffffu / (unsigned)d_ + 1u), d(d_) {}
   __device__ __forceinline__ int div(int i) const { return d == 1 ? i : (int)__umulhi((unsigned)i, m); }
 };
-
-// Exact small-integer <-> float conversions on the FMA / ALU pipes (I2F / F2I issue on the quarter-rate XU pipe and
-// there are ~0.8 M of them per image): 2^23 + n has n in its low mantissa bits for 0 <= n < 2^23.
-__device__ __forceinline__ float u8f(unsigned word, int k) {   // (float) byte k of word
-  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (unsigned)k)), 8388608.0f);
-}
-__device__ __forceinline__ float small_int_to_float(int n) {   // 0 <= n < 2^23
-  return __fsub_rn(__uint_as_float(0x4B000000u | (unsigned)n), 8388608.0f);
-}
-__device__ __forceinline__ int trunc_small_float(float x) {    // (int)x for 0 <= x < 2^22 (round toward zero = floor)
-  return (int)(__float_as_uint(__fadd_rz(x, 8388608.0f)) & 0x7fffffu);
-}
 
 template <bool kBf16>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
@@ -644,6 +567,12 @@ __global__ void div255_selftest_kernel(unsigned long long* mismatches) {
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 }  // namespace
+
+// preprocess_stream.cu
+bool preprocess_stream_supported(const uint8_t* src, int Hs, int Ws, const int32_t* crop, const int32_t* jq, int Ho, int Wo,
+                                 const void* dst, int dst_dtype);
+int preprocess_stream(const uint8_t* src, int N, int Hs, int Ws, const uint8_t* flags, int Ho, int Wo, void* dst, int dst_dtype,
+                      cudaStream_t st);
 }  // namespace vip
 
 extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const int32_t* crop_yxhw,
@@ -662,6 +591,12 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
   const bool jpeg = jpeg_q != nullptr;
   VIP_REQUIRE(!jpeg || (Ho <= 256 && Wo <= 256), VIP_ERR_UNSUPPORTED,
               "vip_preprocess: JPEG emulation needs Ho, Wo <= 256 (planes live in shared memory)");
+  // plain resize / normalise / flips (what main.py runs): the streaming kernel; VIP_PRE_STREAM=0 keeps the fused kernel
+  static const bool stream_on = [] { const char* v = getenv("VIP_PRE_STREAM"); return v == nullptr || v[0] != '0'; }();
+  if (stream_on && preprocess_stream_supported(src, Hs, Ws, crop_yxhw, jpeg_q, Ho, Wo, dst, dst_dtype)) {
+    const int rc = preprocess_stream(src, N, Hs, Ws, flags, Ho, Wo, dst, dst_dtype, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (rc <= 0) return rc;   // rc > 0: geometry too wide for the streaming kernel's shared memory -> fused kernel
+  }
 
   PreArgs a{};
   a.src = src; a.crop = crop_yxhw; a.jq = jpeg_q; a.flags = flags; a.dst = dst;

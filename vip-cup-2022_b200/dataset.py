@@ -72,7 +72,9 @@ class DeviceDataset:
         self.paths, self.batch_size, self.img_size = list(paths), int(batch_size), tuple(int(v) for v in img_size)
         self.decode_fn, self.augment_fn, self.augment = decode_fn, augment_fn, augment
         self.out_dtype, self.device = out_dtype, device
-        self.pool = ThreadPoolExecutor(max_workers=workers)
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        # the prefetch task waits for the decode tasks: it needs a thread of its own (a single-worker pool would deadlock)
+        self.prefetcher = ThreadPoolExecutor(max_workers=1)
 
     def __len__(self):
         return -(-len(self.paths) // self.batch_size)
@@ -81,19 +83,40 @@ class DeviceDataset:
         imgs = list(self.pool.map(self.decode_fn, paths))
         return imgs
 
-    def __iter__(self):
+    def host_batches(self, depth=2):
+        """One pass over the images as (first index, [decoded uint8 HxWx3 arrays]) per batch; the next ``depth`` batches
+        are being decoded on the thread pool while the caller works on the current one (tf.data prefetch,
+        dataset/dataset.py:100)."""
         n = len(self.paths)
-        nxt = self.pool.submit(self._decode_batch, self.paths[: self.batch_size]) if n else None
-        for i0 in range(0, n, self.batch_size):
-            imgs = nxt.result()
-            i1 = min(n, i0 + self.batch_size)
-            if i1 < n:  # prefetch: decode of the next batch overlaps this batch's device work
-                nxt = self.pool.submit(self._decode_batch, self.paths[i1: i1 + self.batch_size])
+        starts = list(range(0, n, self.batch_size))
+        pending = [self.prefetcher.submit(self._decode_batch, self.paths[i0: i0 + self.batch_size]) for i0 in starts[:depth]]
+        for k, i0 in enumerate(starts):
+            imgs = pending.pop(0).result()
+            if k + depth < len(starts):
+                j0 = starts[k + depth]
+                pending.append(self.prefetcher.submit(self._decode_batch, self.paths[j0: j0 + self.batch_size]))
+            yield i0, imgs
+
+    def __iter__(self):
+        for _, imgs in self.host_batches(depth=1):
             flags = self.augment_fn(len(imgs)) if self.augment else None
             yield self._to_device(imgs, flags)
 
-    def _to_device(self, imgs, flags):
-        h, w = self.img_size
+    def stage(self, imgs):
+        """Decoded images of ONE size -> pinned uint8 [n,Hs,Ws,3] -> device (async copy on the current stream); None when
+        the sizes differ (the caller then takes the per-size path of ``to_device``)."""
+        shape = imgs[0].shape
+        if any(im.shape != shape for im in imgs):
+            return None
+        st = torch.empty((len(imgs), *shape), dtype=torch.uint8).pin_memory()
+        np.stack(imgs, out=st.numpy())
+        return st.to(self.device, non_blocking=True)
+
+    def to_device(self, imgs, flags, img_size=None):
+        return self._to_device(imgs, flags, img_size)
+
+    def _to_device(self, imgs, flags, img_size=None):
+        h, w = img_size or self.img_size
         out = torch.empty((len(imgs), h, w, 3), dtype=self.out_dtype, device=self.device)
         # group by decoded size (test images may have other dimensions, dataset.py:32-34)
         groups = {}

@@ -37,6 +37,7 @@ def _rel_index(ws):  # attention.py:39-50
 
 
 FUSED_MLP = os.environ.get("VIP_FUSED_MLP", "1") != "0"   # level-0 MLPs through vip_mlp_fused_bf16
+TWO_PLANE = os.environ.get("VIP_TWO_PLANE", "1") != "0"   # hi + lo bf16 planes for the block residual stream
 
 
 def _pad_rows(a, mult=32):  # [N, K] -> N rounded up to `mult` with zero rows
@@ -216,7 +217,7 @@ class GCViT:
     def _mb_apply(self, x, d):
         """x + [pad1 -> DW3x3 -> GELU -> SE -> Conv1x1](x)   (feature.py:105-109,144-150)"""
         b, h, w, c = x.shape
-        gap = nn.zero_(torch.empty((b, c), dtype=torch.float32, device=x.device))
+        gap = nn.zero_(torch.empty((b, c), dtype=nn.STATS, device=x.device))
         y = nn.dwconv3x3(x, d["dw"], gelu=True, gap=gap)        # SE squeeze accumulated by the same kernel
         pooled = nn.scale_cast_bf16(gap, 1.0 / (h * w))
         hid = nn.gemm(pooled, d["fc0"], act="gelu")
@@ -235,23 +236,29 @@ class GCViT:
         x = nn.conv2d(x, d["red"], None, ksize=3, stride=stride, pad=1)
         return nn.layernorm(x, *d["n2"], eps=LN_EPS, row_stats=out_stats)
 
-    def _block(self, x, stats, d, heads, ws, q_global, st_mid, st_out):
+    def _block(self, x, x_lo, stats, d, heads, ws, q_global, st_mid, st_out):
         """GCViTBlock (block.py:60-81).  Both LayerNorms are folded into the contraction that consumes them: ``stats`` holds
-        (sum, sum^2) of the rows of x, the proj / fc2 epilogues emit the statistics of their outputs."""
+        the row statistics records of x, the proj / fc2 epilogues emit the records of their outputs.  The residual stream
+        is carried in two bf16 planes (x = hi + lo, 16 mantissa bits): the hi plane is the operand of qkv / fc1, the lo
+        plane only meets the proj / fc2 epilogues, so 2 x depth bf16 roundings of the running sum do not pile up
+        (SURVEY.md 7 "fp32 residual stream if needed"; measured: 1.5e-2 -> 4e-3 logit error on GCViT-small)."""
         b, h, w, c = x.shape
         x2 = x.view(-1, c)
         wq, bq, cq = d["qkv"]
         qkv = nn.gemm(x2, wq, bias=bq, ln_stats=stats, ln_colsum=cq, ln_cols=c, ln_eps=LN_EPS)
         a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
-        x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=st_mid)
+        lo1 = torch.empty_like(x2) if TWO_PLANE else None
+        x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=st_mid, residual_lo=x_lo, out_lo=lo1)
         w1, b1, c1 = d["fc1"]
         if FUSED_MLP and (c, w1.shape[0]) in nn.MLP_FUSED_SHAPES:
             # narrow levels: both contractions in one kernel, the [tokens, hidden] tensor never reaches HBM
-            x2 = nn.mlp_fused(x2, st_mid, w1, c1, b1, *d["fc2"], ln_eps=LN_EPS, row_stats=st_out)
+            res = nn.mlp_fused(x2, st_mid, w1, c1, b1, *d["fc2"], ln_eps=LN_EPS, row_stats=st_out, x_lo=lo1, want_lo=TWO_PLANE)
+            x2, lo2 = res if TWO_PLANE else (res, None)
         else:
             hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
-            x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out)
-        return x2.view(b, h, w, c)
+            lo2 = torch.empty_like(x2) if TWO_PLANE else None
+            x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out, residual_lo=lo1, out_lo=lo2)
+        return x2.view(b, h, w, c), lo2
 
     def features(self, x, taps=None):
         p, cfg = self.p, self.cfg
@@ -263,8 +270,8 @@ class GCViT:
             x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
         nimg = x.shape[0]
 
-        def level_stats(i, tokens):  # one zeroed arena per level: [1 + 2*depth, tokens, 2]
-            return nn.zero_(torch.empty((1 + 2 * cfg["depths"][i], tokens, 2), dtype=torch.float32, device=x.device))
+        def level_stats(i, tokens):  # one zeroed arena of row statistics records per level: [1 + 2*depth, tokens, 3]
+            return nn.row_stats_buffer(1 + 2 * cfg["depths"][i], tokens, device=x.device)
 
         h0 = (x.shape[1] + 2 - 3) // self.first_strides + 1
         st = level_stats(0, nimg * h0 * h0)
@@ -283,8 +290,10 @@ class GCViT:
                 if not keep:
                     q = nn.maxpool3s2(q)
             q = q.view(b, ws * ws, c)
+            x_lo = None   # the level starts from a LayerNorm output: low plane = 0
             for j in range(depth):
-                x = self._block(x, st[2 * j], p[f"b{i}_{j}"], heads, ws, q if j % 2 else None, st[2 * j + 1], st[2 * j + 2])
+                x, x_lo = self._block(x, x_lo, st[2 * j], p[f"b{i}_{j}"], heads, ws, q if j % 2 else None, st[2 * j + 1],
+                                      st[2 * j + 2])
             if i < 3:
                 ho = (h + 2 - 3) // 2 + 1
                 st = level_stats(i + 1, b * ho * ho)

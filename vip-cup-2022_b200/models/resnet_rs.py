@@ -193,7 +193,7 @@ class ResNetRS:
             taps["stem"] = x
         nimg = x.shape[0]
         nblocks = sum(r for _, r in BLOCK_ARGS[self.depth])
-        gaps = nn.zero_(torch.empty((nblocks, nimg, 512), dtype=torch.float32, device=x.device))  # one memset
+        gaps = nn.zero_(torch.empty((nblocks, nimg, 512), dtype=nn.STATS, device=x.device))  # one memset (fixed-point sums)
         k = 0
         for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
             for bi in range(reps):

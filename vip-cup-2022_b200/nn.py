@@ -26,12 +26,24 @@ def _chk(t, name, dtype=BF16):
         raise VipError(f"{name} must be a contiguous CUDA {dtype} tensor")
 
 
+STATS = torch.int64   # row statistics records [M, 3] and pooled sums are 64-bit fixed point (csrc/stats.cuh)
+
+
+def row_stats_buffer(*lead, device):
+    """Zeroed row statistics records: int64 [*lead, 3] = (sum (v - p), sum (v - p)^2 in 36.28 fixed point, bits of p)."""
+    return zero_(torch.empty((*lead, 3), dtype=STATS, device=device))
+
+
 def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=None, ln_colsum=None, ln_cols=0,
-              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0, row_gate=None, gate_rows=0):
-    _chk(residual, "residual")
-    for name, t in (("bias", bias), ("colscale", colscale), ("ln_stats", ln_stats), ("ln_colsum", ln_colsum),
-                    ("row_stats", row_stats), ("gap", gap), ("row_gate", row_gate)):
+              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0, row_gate=None, gate_rows=0, residual_lo=None, out_lo=None):
+    _chk(residual, "residual"), _chk(residual_lo, "residual_lo"), _chk(out_lo, "out_lo")
+    for name, t in (("bias", bias), ("colscale", colscale), ("ln_colsum", ln_colsum), ("row_gate", row_gate)):
         _chk(t, name, torch.float32)
+    for name, t in (("ln_stats", ln_stats), ("row_stats", row_stats), ("gap", gap)):
+        _chk(t, name, STATS)
+    for name, t in (("ln_stats", ln_stats), ("row_stats", row_stats)):
+        if t is not None and (t.shape[-1] != 3 or t.numel() != 3 * out.shape[0]):
+            raise VipError(f"{name} must be int64 [M, 3] row statistics records")
     e = _lib.Epilogue()
     e.bias, e.act, e.colscale = _p(bias), ACT[act], _p(colscale)
     e.residual, e.ldr = _p(residual), (0 if residual is None else residual.stride(0))
@@ -40,6 +52,7 @@ def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=N
     e.ln_stats, e.ln_colsum, e.ln_cols, e.ln_eps = _p(ln_stats), _p(ln_colsum), int(ln_cols), float(ln_eps)
     e.row_stats, e.gap, e.gap_rows = _p(row_stats), _p(gap), int(gap_rows)
     e.row_gate, e.gate_rows = _p(row_gate), int(gate_rows)
+    e.residual_lo, e.out_lo = _p(residual_lo), _p(out_lo)
     return e
 
 
@@ -179,7 +192,7 @@ def scale_add_act(y, gate=None, shortcut=None, act=None, out=None):
 
 def layernorm(x, gamma, beta, eps=1e-5, row_stats=None):
     _chk(x, "x"), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32)
-    _chk(row_stats, "row_stats", torch.float32)
+    _chk(row_stats, "row_stats", STATS)
     c = x.shape[-1]
     out = torch.empty_like(x)
     _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), _p(row_stats), x.numel() // c, c, eps,
@@ -188,8 +201,9 @@ def layernorm(x, gamma, beta, eps=1e-5, row_stats=None):
 
 
 def dwconv3x3(x, w, gelu=False, gap=None):
-    """gap: f32 [N,C] zeroed accumulator that receives the per-image channel sums of the output (fused SE squeeze)."""
-    _chk(x, "x"), _chk(w, "w", torch.float32), _chk(gap, "gap", torch.float32)
+    """gap: int64 [N,C] zeroed fixed-point accumulator that receives the per-image channel sums of the output (fused SE
+    squeeze)."""
+    _chk(x, "x"), _chk(w, "w", torch.float32), _chk(gap, "gap", STATS)
     n, h, wd, c = x.shape
     out = torch.empty_like(x)
     _lib.check(_lib.lib().vip_dwconv3x3_bf16(_p(x), _p(w), _p(out), _p(gap), n, h, wd, c, int(gelu), _st()),
@@ -235,24 +249,28 @@ def cast_bf16(x_f32):
 MLP_FUSED_SHAPES = {(96, 192), (64, 192)}
 
 
-def mlp_fused(x, ln_stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=None):
+def mlp_fused(x, ln_stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=None, x_lo=None, want_lo=False):
     """x + fc2(gelu(fc1(LayerNorm(x)))) in one kernel (hidden activations stay on the SM); arguments as for the two
     ``gemm`` calls it replaces: w1 [hidden, C] gamma-scaled + colsum1 + bias1 (LayerNorm folded), w2 [C, hidden] + bias2.
-    Only for (C, hidden) in MLP_FUSED_SHAPES."""
-    _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2"), _chk(ln_stats, "ln_stats", torch.float32)
+    Only for (C, hidden) in MLP_FUSED_SHAPES.  ``x_lo`` / ``want_lo``: low planes of the two-plane residual stream;
+    with want_lo returns (out, out_lo)."""
+    _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2"), _chk(ln_stats, "ln_stats", STATS), _chk(x_lo, "x_lo")
+    _chk(row_stats, "row_stats", STATS)
     m, c = x.shape
     hidden = w1.shape[0]
     out = torch.empty_like(x)
-    rc = _lib.lib().vip_mlp_fused_bf16(_p(x), m, c, hidden, _p(ln_stats), float(ln_eps), _p(w1), w1.stride(0), _p(colsum1),
-                                       _p(bias1), _p(w2), w2.stride(0), _p(bias2), _p(out),
-                                       _p(row_stats) if row_stats is not None else None, _st())
+    out_lo = torch.empty_like(x) if want_lo else None
+    rc = _lib.lib().vip_mlp_fused_bf16(_p(x), _p(x_lo), m, c, hidden, _p(ln_stats), float(ln_eps), _p(w1), w1.stride(0),
+                                       _p(colsum1), _p(bias1), _p(w2), w2.stride(0), _p(bias2), _p(out), _p(out_lo),
+                                       _p(row_stats), _st())
     _lib.check(rc, "vip_mlp_fused_bf16")
-    return out
+    return (out, out_lo) if want_lo else out
 
 
-def scale_cast_bf16(x_f32, scale):
-    _chk(x_f32, "x", torch.float32)
-    out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
-    _lib.check(_lib.lib().vip_scale_cast_f32_bf16(_p(x_f32), float(scale), _p(out), x_f32.numel(), _st()),
-               "vip_scale_cast_f32_bf16")
+def scale_cast_bf16(x_fx, scale):
+    """bf16(x * scale) of fixed-point pooled sums (int64, csrc/stats.cuh): the SE squeeze mean as a GEMM operand."""
+    _chk(x_fx, "x", STATS)
+    out = torch.empty(x_fx.shape, dtype=BF16, device=x_fx.device)
+    _lib.check(_lib.lib().vip_scale_cast_fx_bf16(_p(x_fx), float(scale), _p(out), x_fx.numel(), _st()),
+               "vip_scale_cast_fx_bf16")
     return out

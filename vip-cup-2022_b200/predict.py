@@ -22,6 +22,8 @@ def model_name_of(model_paths):
 
 def aggregate_model(pred_passes, tta, n, agg="mean"):
     """main.py:110-114 on a float32 [tta*n, k] array: TTA mean, multi-class -> binary P(synthetic)."""
+    if n == 0:                       # a rank whose shard is empty (more ranks than images)
+        return np.zeros((0, 1), np.float32)
     pred = pred_passes[: tta * n, :]
     pred = getattr(np, agg)(pred.reshape((tta, n, -1)), axis=0)
     if pred.shape[1] > 1:
@@ -47,7 +49,9 @@ def ensemble_frame(test_csv, test_names, per_model_preds, thr, agg="mean"):
 
 
 def predict_model(model, dtest, tta):
-    """All TTA passes of one fold: returns float32 [tta * n_local, k] on the host (one D2H copy)."""
+    """All TTA passes of one fold, eagerly, batch by batch (``model.predict(dtest, steps)``, main.py:109): returns float32
+    [tta * n_local, k] on the host (one D2H copy).  ``predict_soln`` uses the graph-captured :class:`GraphedModel` path
+    instead; this stays as the plain operator seam."""
     outs = []
     for _ in range(max(int(tta), 1)):
         for batch in dtest:
@@ -55,6 +59,129 @@ def predict_model(model, dtest, tta):
     if not outs:
         return np.zeros((0, 1), np.float32)
     return torch.cat(outs, dim=0).float().cpu().numpy()
+
+
+class SharedInput:
+    """Static device buffers one batch of decoded images lands in; every GraphedModel of the same batch size reads them."""
+
+    def __init__(self, batch, src_hw, device):
+        self.batch, self.src_hw = int(batch), tuple(src_hw)
+        self.src = torch.zeros((self.batch, *self.src_hw, 3), dtype=torch.uint8, device=device)
+        self.flags = torch.zeros((self.batch,), dtype=torch.uint8, device=device)
+
+
+class GraphedModel:
+    """One fold of one model at a fixed batch size: decoded uint8 batch -> fused preprocessing to the model's resolution
+    (dataset/dataset.py:31-37 + the flip / gray flags of dataset/augment.py:115-120,142-146) -> forward -> probabilities,
+    captured ONCE as a CUDA graph (~250 kernel launches per replay instead of ~250 ctypes calls per batch).  Ragged tail
+    batches and batches of another source size run the same code eagerly."""
+
+    def __init__(self, model, dim, shared: SharedInput, use_graph=True):
+        from . import ops
+
+        self.model, self.dim, self.shared, self._ops = model, tuple(int(v) for v in dim), shared, ops
+        self.graph, self.probs = None, None
+        if use_graph:
+            dev = shared.src.device
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                self.forward(shared.src, shared.flags)          # warm-up: lazy kernel attributes, allocator pools
+                torch.cuda.synchronize(dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=s):
+                    self.probs = self.forward(shared.src, shared.flags)
+            torch.cuda.current_stream(dev).wait_stream(s)
+
+    def forward(self, src, flags):
+        return self.model(self._ops.preprocess(src, self.dim, None, None, flags, out_dtype=torch.bfloat16))
+
+    def __call__(self, src, flags):
+        """src uint8 [b,Hs,Ws,3] on the device, flags uint8 [b] or None -> float32 [b,k] (valid until the next call)."""
+        sh = self.shared
+        if self.graph is not None and tuple(src.shape) == tuple(sh.src.shape):
+            if src.data_ptr() != sh.src.data_ptr():
+                sh.src.copy_(src, non_blocking=True)
+            if flags is None:
+                sh.flags.zero_()
+            elif flags.data_ptr() != sh.flags.data_ptr():
+                sh.flags.copy_(flags, non_blocking=True)
+            self.graph.replay()
+            return self.probs
+        return self.forward(src, flags)
+
+
+def _load_model(model_name, model_path, dim, device):
+    W, meta = registry.load_checkpoint(model_path)
+    head_k = W["predictions/kernel" if "predictions/kernel" in W else "head/kernel"].shape[1]
+    model = registry.create_model(model_name, dim, num_classes=head_k,
+                                  head_act=meta["head_act"] or ("sigmoid" if head_k == 1 else "softmax"), device=device)
+    return model.load_weights(W)
+
+
+def predict_device(CFG, local_paths, tta, verbose=False):
+    """Device half of ``predict_soln`` for this rank's shard: every fold of every registry entry over ``local_paths``.
+    Returns (list over (model, fold) of float32 [tta * n_local, k] arrays, pass-major like ``model.predict`` on the
+    repeated dataset (main.py:109-111), fold counts per model).
+
+    Loop order: the reference runs model-major (decode the whole set once per model); here the decoded batch is the outer
+    loop and every fold of every model consumes it while the thread pool decodes the next ones -- each JPEG is decoded once
+    per TTA pass whatever the ensemble size.  Per-image results do not depend on the order or on the batch an image is in
+    (integer-atomic statistics, see csrc/stats.cuh), so the outputs are the same."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_local = len(local_paths)
+    entries, fold_counts = [], []
+    for model_idx, (model_paths, dim, idx) in enumerate(CFG.ckpt_cfg):
+        model_name = model_name_of(model_paths)
+        bs = 8 * registry.NAME2BS.get(model_name, 16)                 # main.py:85
+        bs = int(os.environ.get("VIP_DEVICE_BATCH", bs))              # throughput knob only: results are batch-independent
+        if verbose:
+            print(f"> MODEL({model_idx + 1}/{len(CFG.ckpt_cfg)}): {model_name} | DIM: {dim}")
+            print("> BATCH SIZE : ", bs)
+        for model_path in sorted(model_paths):
+            entries.append(dict(name=model_name, dim=tuple(dim), bs=bs, path=model_path))
+        fold_counts.append(len(model_paths))
+    if n_local == 0:
+        return [np.zeros((0, 1), np.float32) for _ in entries], fold_counts
+    chunk = max(e["bs"] for e in entries)
+    CFG.batch_size, CFG.img_size = chunk, entries[0]["dim"]
+    ds = build_dataset(local_paths, labels=None, augment=tta > 1, repeat=True, cache=False, shuffle=False,
+                       batch_size=chunk, drop_remainder=False, CFG=CFG, device=dev)
+    shared, outs = {}, []
+    use_graph = os.environ.get("VIP_GRAPH", "1") != "0"
+    for _ in range(tta):
+        for i0, imgs in ds.host_batches():
+            flags_h = ds.augment_fn(len(imgs)) if tta > 1 else None
+            src = ds.stage(imgs)
+            flags = None if flags_h is None else torch.from_numpy(np.ascontiguousarray(flags_h)).to(dev, non_blocking=True)
+            for e in entries:
+                if "runner" not in e:           # first batch: weights to the device, graph capture at this source size
+                    model = _load_model(e["name"], e["path"], e["dim"], dev)
+                    if src is not None and n_local >= e["bs"]:
+                        key = (e["bs"], tuple(src.shape[1:3]))
+                        if key not in shared:
+                            shared[key] = SharedInput(e["bs"], key[1], dev)
+                        e["runner"] = GraphedModel(model, e["dim"], shared[key], use_graph=use_graph)
+                    else:
+                        e["runner"] = GraphedModel(model, e["dim"], SharedInput(1, (8, 8), dev), use_graph=False)
+                    e["out"] = None
+                r = e["runner"]
+                if src is None:                  # mixed source sizes in this batch: per-size preprocessing, eager forward
+                    probs = [r.model(ds.to_device(imgs, flags_h, e["dim"]))]
+                else:
+                    probs = []
+                    for j0 in range(0, len(imgs), e["bs"]):
+                        pj = r(src[j0: j0 + e["bs"]], None if flags is None else flags[j0: j0 + e["bs"]])
+                        probs.append(pj.clone() if pj is r.probs else pj)
+                pr = probs[0] if len(probs) == 1 else torch.cat(probs, 0)
+                if e["out"] is None:
+                    e["out"] = torch.empty((tta * n_local, pr.shape[1]), dtype=torch.float32, device=dev)
+                    e["pos"] = 0
+                e["out"][e["pos"]: e["pos"] + pr.shape[0]] = pr
+                e["pos"] += pr.shape[0]
+    for e in entries:
+        outs.append(e["out"].cpu().numpy())
+    return outs, fold_counts
 
 
 def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None):
@@ -78,32 +205,18 @@ def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None):
     n_local = hi - lo
     tta = max(int(CFG.tta), 1)
 
-    local_rows, fold_counts = [], []
-    for model_idx, (model_paths, dim, idx) in enumerate(CFG.ckpt_cfg):
-        model_name = model_name_of(model_paths)
-        if verbose:
-            print(f"> MODEL({model_idx + 1}/{len(CFG.ckpt_cfg)}): {model_name} | DIM: {dim}")
-        CFG.batch_size = 8 * registry.NAME2BS.get(model_name, 16)   # main.py:85
-        if verbose:
-            print("> BATCH SIZE : ", CFG.batch_size)
-        CFG.img_size = dim
-        dtest = None
-        for model_path in sorted(model_paths):
-            if predict_fn is not None:
-                pred = predict_fn(model_name, model_path, dim, local_paths)
-            else:
-                if dtest is None:
-                    dtest = build_dataset(local_paths, labels=None, augment=CFG.tta > 1, repeat=True, cache=False,
-                                          shuffle=False, batch_size=CFG.batch_size, drop_remainder=False, CFG=CFG)
-                W, meta = registry.load_checkpoint(model_path)
-                head_k = W["predictions/kernel" if "predictions/kernel" in W else "head/kernel"].shape[1]
-                model = registry.create_model(model_name, dim, num_classes=head_k,
-                                              head_act=meta["head_act"] or ("sigmoid" if head_k == 1 else "softmax"))
-                model.load_weights(W)
-                pred = predict_model(model, dtest, tta)
-                del model
-            local_rows.append(aggregate_model(np.asarray(pred, np.float32), tta, n_local, CFG.agg)[:, 0])
-        fold_counts.append(len(model_paths))
+    if predict_fn is not None:
+        raw, fold_counts = [], []
+        for model_idx, (model_paths, dim, idx) in enumerate(CFG.ckpt_cfg):
+            model_name = model_name_of(model_paths)
+            CFG.batch_size = 8 * registry.NAME2BS.get(model_name, 16)   # main.py:85
+            CFG.img_size = dim
+            for model_path in sorted(model_paths):
+                raw.append(predict_fn(model_name, model_path, dim, local_paths))
+            fold_counts.append(len(model_paths))
+    else:
+        raw, fold_counts = predict_device(CFG, local_paths, tta, verbose)
+    local_rows = [aggregate_model(np.asarray(pred, np.float32), tta, n_local, CFG.agg)[:, 0] for pred in raw]
 
     # one exchange step: [sum(folds), n_local] float32 per rank -> [sum(folds), N] everywhere
     dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and strategy.backend != "gloo" \
@@ -117,6 +230,11 @@ def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None):
         for fc in fold_counts:
             per_model.append([full[r + f][:, None] for f in range(fc)])
             r += fc
+        if os.environ.get("VIP_SAVE_PROBS", "0") == "1" and getattr(CFG, "temp_save_dir", None):
+            # the per-model prediction files the reference has commented out (main.py:124,129): P(synthetic), fold mean
+            for (model_paths, _, _), folds in zip(CFG.ckpt_cfg, per_model):
+                pd.DataFrame({"filename": test_names, "logit": getattr(np, CFG.agg)(folds, axis=0)[:, 0]}).to_csv(
+                    os.path.join(CFG.temp_save_dir, model_name_of(model_paths) + "_pred.csv"), index=False)
         if ensemble:
             pred_df = ensemble_frame(test_csv, test_names, per_model, CFG.thr, CFG.agg)
             pred_df.to_csv(CFG.output_csv_path, index=False)
