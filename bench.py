@@ -16,7 +16,16 @@ one batch; the whole step is one CUDA graph.
                 measured sustained bf16 peak; the tcgen05 GEMM / implicit-conv kernel is the dominant kernel
   preprocess_only  BASELINE.json configs[1] (augment pipeline on a 4096-image batch, HBM-bound declaration) with its own
                 roofline object -- the kernel `roofline.traffic` was captured for
-  cpu_baseline  the CPU oracle (oracle/: numpy preprocessing + PyTorch-CPU fp32 backbones) on a bounded sample (rank 0, N=1)
+  preprocess_nojpeg  the preprocessing main.py actually runs (no crop, no JPEG emulation): the streaming kernel at
+                4096 images, 200->224 f32 / bf16 and 200->200 bf16, each against the HBM roofline
+  gcvit_tiny_b256  BASELINE.json configs[2] (GCViT-tiny 224x224 bf16 forward, batch 256) with its own tensor roofline
+  main_py_config0  configs[0] through the product's predict_soln (64 synthetic JPEG files, ResNet-RS-50, host decode,
+                H2D, CUDA graphs, D2H, pandas epilogue): wall-clock images/s, cold (weights + graph capture) and warm
+  main_py_config4  configs[4]: 5000 synthetic JPEG files, RS-101 + GCViT-small + RS-50, 2-pass flip TTA, sharded over
+                the --gpus ranks with the NCCL all_gather of the result (strong scaling), plus the host decode rate alone
+                -- the limiter of the end-to-end run
+  cpu_baseline  the CPU oracle (oracle/: numpy preprocessing + PyTorch-CPU fp32 backbones) on a bounded sample (rank 0, N=1),
+                and configs[0] exactly (64 JPEGs, RS-50, batch 16) with decode+preprocess and forward timed separately
 
 ``--impl reference`` times the CPU restatement of the reference path on all host cores (the TensorFlow reference itself
 cannot be installed offline) and prints the same line with "impl": "reference".
@@ -145,6 +154,32 @@ def _oracle_step(n_images: int, threads: int):
     return time.perf_counter() - t0
 
 
+def parity_sample(pred, dev, n=16):
+    """Checker leg (outside the timed region): n oracle images go into the benched batch, the step runs as benched (same
+    graph, same batch size), and the ensemble P(synthetic) is compared with the fp32 CPU oracle on the same weights."""
+    import numpy as np
+    import torch
+
+    from oracle import gcvit as G
+    from oracle import preprocess as P
+    from oracle import resnet_rs as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    imgs = np.stack([P.synth_image(500 + i, HS, WS) for i in range(n)])
+    pos = np.random.default_rng(3).choice(BATCH, n, replace=False)
+    keep = pred.src[torch.from_numpy(pos).to(dev)].clone()
+    pred.src[torch.from_numpy(pos).to(dev)] = torch.from_numpy(imgs).to(dev)
+    pred.run()
+    torch.cuda.synchronize()
+    got = pred.acc.cpu().numpy()[pos]
+    pred.src[torch.from_numpy(pos).to(dev)] = keep
+    p1 = R.forward(np.stack([P.decode_to_float(im, 200, 200) for im in imgs]), R.random_weights(101, 2, seed=0), 101, head_act="softmax")
+    p2 = G.forward(np.stack([P.decode_to_float(im, 224, 224) for im in imgs]), G.random_weights("small", 2, seed=0), "small",
+                   head_act="softmax")
+    ref = np.mean([1.0 - p1[:, 0].astype(np.float64), 1.0 - p2[:, 0].astype(np.float64)], axis=0)
+    return float(np.abs(got - ref).max())
+
+
 def cpu_baseline(threads: int, budget_s: float = 20.0):
     """Oracle throughput on a bounded sample (about ``budget_s`` of CPU work).  Returns (images/s, sample description)."""
     n0 = 2
@@ -153,6 +188,47 @@ def cpu_baseline(threads: int, budget_s: float = 20.0):
     n = int(max(2, min(64, budget_s / max(t / n0, 1e-3))))
     t = _oracle_step(n, threads)
     return n / t, f"{n} images of the 1024-image batch (after a 2-image warm-up), {threads} torch threads"
+
+
+def cpu_baseline_config0(threads: int):
+    """BASELINE.md section 3, configs[0] exactly: 64 synthetic 200x200 JPEGs, ResNet-RS-50 random-init, batch 16, on the CPU
+    oracle; decode + preprocess and forward timed separately (1 warm-up batch, median of 3 runs)."""
+    import io
+
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from oracle import preprocess as P
+    from oracle import resnet_rs as R
+
+    torch.set_num_threads(threads)
+    W = R.random_weights(50, 2, seed=0)
+    blobs = []
+    for i in range(64):
+        buf = io.BytesIO()
+        Image.fromarray(P.synth_image(i)).save(buf, format="JPEG", quality=65 + i % 35, subsampling=2)
+        blobs.append(buf.getvalue())
+
+    def decode(lo, hi):
+        return np.stack([P.decode_to_float(np.asarray(Image.open(io.BytesIO(b)).convert("RGB")), 200, 200) for b in blobs[lo:hi]])
+
+    R.forward(decode(0, 16), W, 50, head_act="softmax")
+    runs = []
+    for _ in range(3):
+        t_pre = t_fwd = 0.0
+        for lo in range(0, 64, 16):
+            t0 = time.perf_counter()
+            x = decode(lo, lo + 16)
+            t1 = time.perf_counter()
+            R.forward(x, W, 50, head_act="softmax")
+            t_pre, t_fwd = t_pre + (t1 - t0), t_fwd + (time.perf_counter() - t1)
+        runs.append((t_pre + t_fwd, t_pre, t_fwd))
+    tot, t_pre, t_fwd = sorted(runs)[1]
+    return {"workload": "configs[0]: 64 JPEGs, ResNet-RS-50, batch 16 (restated CPU oracle: Pillow decode + numpy preprocess, "
+                        "PyTorch-CPU fp32 forward; not TensorFlow)", "images_per_s": 64 / tot,
+            "decode_preprocess_images_per_s": 64 / t_pre, "forward_images_per_s": 64 / t_fwd, "cores": threads,
+            "torch_threads": torch.get_num_threads()}
 
 
 def run_reference(args):
@@ -219,6 +295,216 @@ def bench_preprocess_only(dev, steps):
     return ms
 
 
+def _time_launch(fn, steps):
+    import torch
+
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_preprocess_nojpeg(dev, steps, hbm_peak):
+    """What main.py runs per batch (dataset/dataset.py:31-37): u8 [4096,200,200,3] -> resize -> /255, no crop / JPEG."""
+    import numpy as np
+    import torch
+
+    from vipcup_b200 import ops
+
+    rng = np.random.default_rng(99)
+    src = torch.from_numpy(rng.integers(0, 256, (PRE_N, HS, WS, 3), dtype=np.uint8)).to(dev)   # 492 MB > L2
+    out = {}
+    for tag, hw, dt in (("resize224_f32", 224, torch.float32), ("resize224_bf16", 224, torch.bfloat16),
+                        ("identity200_bf16", 200, torch.bfloat16)):
+        dst = torch.empty((PRE_N, hw, hw, 3), dtype=dt, device=dev)
+        ms = _time_launch(lambda: ops.preprocess(src, (hw, hw), None, None, None, out_dtype=dt, out=dst), steps)
+        nbytes = PRE_N * (HS * WS * 3 + hw * hw * 3 * dst.element_size())
+        ach = nbytes / (ms * 1e-3) / 1e9
+        out[tag] = {"ms_per_launch": ms, "images_per_s": PRE_N / (ms * 1e-3), "algorithmic_bytes_per_launch": nbytes,
+                    "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
+        del dst
+    out["kernel"] = "resize_stream_kernel (csrc/preprocess_stream.cu)"
+    return out
+
+
+def bench_gcvit_tiny_b256(dev, steps, tc_peak):
+    """BASELINE.json configs[2]: GCViT-tiny 224x224 bf16 forward, batch 256, random-init weights, one CUDA graph."""
+    import torch
+
+    from vipcup_b200 import registry
+
+    b = 256
+    model = registry.create_model("GCViTTiny-224x224", (224, 224), num_classes=2, device=dev).init_random(seed=0)
+    x = torch.rand((b, 224, 224, 3), device=dev).to(torch.bfloat16)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        model(x)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            probs = model(x)
+    torch.cuda.current_stream(dev).wait_stream(s)
+    ms = _time_launch(g.replay, steps)
+    tf = 9.52 * b / ms     # GFLOP / ms = TFLOP/s (BASELINE.md section 2: 9.52 GFLOP per image)
+    ok = bool(torch.isfinite(probs).all())
+    del g
+    return {"workload": "configs[2]: GCViT-tiny 224x224 bf16 forward, batch 256, random-init, one CUDA graph",
+            "ms_per_step": ms, "images_per_s": b / (ms * 1e-3), "finite_outputs": ok,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": tf / tc_peak,
+                         "algorithmic_flops_per_step": 9.52e9 * b}}
+
+
+def _write_synth_jpegs(out_dir, n, unique):
+    """n JPEG files (200x200, 4:2:0, quality 65..99) named %05d.jpg + input.csv; ``unique`` distinct images, the rest are
+    hard links to them (same decode work per file).  Plain numpy + Pillow: synthetic inputs, not the oracle."""
+    import numpy as np
+    from PIL import Image
+
+    os.makedirs(out_dir, exist_ok=True)
+    names = []
+    for i in range(n):
+        name = f"{i:05d}.jpg"
+        path = os.path.join(out_dir, name)
+        if i < unique:
+            rng = np.random.default_rng(20221000 + i)
+            base = rng.random((27, 27, 3))
+            img = np.kron(base, np.ones((8, 8, 1)))[:HS, :WS]
+            img = (img + np.roll(img, 3, 0) + np.roll(img, 3, 1) + np.roll(img, (2, 2), (0, 1))) / 4.0
+            img = img * 0.8 + rng.random((HS, WS, 3)) * rng.uniform(0.05, 0.2) + np.linspace(0, 0.2, WS)[None, :, None]
+            img = (img - img.min()) / (img.max() - img.min() + 1e-9)
+            Image.fromarray((img * 255.0 + 0.5).astype(np.uint8)).save(path, quality=int(rng.integers(65, 100)), subsampling=2)
+        else:
+            src = os.path.join(out_dir, f"{i % unique:05d}.jpg")
+            try:
+                os.link(src, path)
+            except OSError:
+                import shutil
+
+                shutil.copyfile(src, path)
+        names.append(name)
+    with open(os.path.join(out_dir, "input.csv"), "w") as f:
+        f.write("filename\n" + "\n".join(names) + "\n")
+
+
+def _write_random_ckpts(model_dir, names, seed0):
+    """Random-init .npz checkpoints (Keras names / layouts) + ckpts.json, from the product models' own initialisers."""
+    import numpy as np
+
+    from vipcup_b200 import registry
+
+    entries = []
+    for i, name in enumerate(names):
+        hw = [int(v) for v in name.rsplit("-", 1)[1].split("x")]
+        d = os.path.join(model_dir, name, "ckpt")
+        os.makedirs(d, exist_ok=True)
+        m = registry.create_model(name, hw, num_classes=2, device="cpu")
+        rng = np.random.default_rng(seed0 + i)
+        W = {}
+        for wname, shp in m.weight_shapes().items():
+            leaf = wname.rsplit("/", 1)[1]
+            if leaf in ("kernel", "depthwise_kernel"):
+                fan_in = int(np.prod(shp[:-1])) if leaf == "kernel" else 9
+                W[wname] = (rng.standard_normal(shp) * np.sqrt(1.0 / fan_in)).astype(np.float32)
+            elif leaf in ("gamma", "moving_variance"):
+                W[wname] = np.ones(shp, np.float32)
+            elif leaf in ("gamma1", "gamma2"):
+                W[wname] = np.full(shp, 0.1, np.float32)
+            elif leaf == "relative_position_bias_table":
+                W[wname] = (rng.standard_normal(shp) * 0.02).astype(np.float32)
+            else:
+                W[wname] = np.zeros(shp, np.float32)
+        np.savez(os.path.join(d, "fold0.npz"), __num_classes__=np.int64(2), __head_act__=np.array("softmax"), **W)
+        entries.append([name, hw, 0])
+    with open(os.path.join(model_dir, "ckpts.json"), "w") as f:
+        json.dump(entries, f)
+
+
+def bench_main_py(tag, n_images, unique, model_names, tta, rank, world, local_rank, dist, device_batch=None):
+    """The product's predict_soln (what ``main.py <in.csv> <out.csv>`` runs, main.py:58-149) on JPEG FILES: host decode
+    (thread pool) -> pinned H2D -> fused preprocessing + backbones (one CUDA graph per model) -> D2H -> NCCL all_gather of
+    the per-model probabilities (world > 1) -> pandas epilogue -> CSV.  Wall clock between barriers, max over ranks.
+    cold = first call (checkpoint load, weight packing, graph capture); warm = second call with the loaded models kept."""
+    import tempfile
+
+    import torch
+
+    from vipcup_b200 import registry
+    from vipcup_b200.config import Config
+    from vipcup_b200.dataset import build_dataset, seeding
+    from vipcup_b200.device import ShardStrategy
+    from vipcup_b200.predict import predict_soln
+
+    root = os.path.join(tempfile.gettempdir(), f"vipcup_bench_{tag}_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}")
+    data, models, out_csv = os.path.join(root, "data"), os.path.join(root, "ckpts"), os.path.join(root, "out", "pred.csv")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        _write_synth_jpegs(data, n_images, unique)
+        _write_random_ckpts(models, model_names, seed0=7)
+        os.makedirs(os.path.dirname(out_csv), exist_ok=True)
+    barrier()
+    if device_batch:
+        os.environ["VIP_DEVICE_BATCH"] = str(device_batch)
+    CFG = Config({})
+    CFG.test_csv, CFG.output_csv_path, CFG.verbose = os.path.join(data, "input.csv"), out_csv, 0
+    CFG.model_dir, CFG.temp_save_dir, CFG.infer_path = models, os.path.join(root, "out"), data
+    CFG.ckpt_cfg = registry.scan_checkpoints(models, os.path.join(models, "ckpts.json"))
+    CFG.debug, CFG.tta, CFG.agg, CFG.resize_method, CFG.num_classes, CFG.seed, CFG.thr = 0, tta, "mean", "bicubic", 1, 42, 0.487
+    strategy = ShardStrategy(rank, world, local_rank, "nccl" if world > 1 else None)
+    cache, times = {}, []
+    for _ in range(2):
+        seeding(CFG)
+        barrier()
+        t0 = time.perf_counter()
+        df = predict_soln(CFG, ensemble=True, strategy=strategy, runner_cache=cache)
+        barrier()
+        times.append(time.perf_counter() - t0)
+    # the host side alone: decode of this rank's shard (one pass), the limiter of the end-to-end run
+    lo, hi, _ = strategy.shard_bounds(n_images)
+    import pandas as pd
+
+    paths = [os.path.join(data, f) for f in pd.read_csv(CFG.test_csv).filename.values[lo:hi]]
+    CFG.img_size = (200, 200)
+    ds = build_dataset(paths, labels=None, augment=False, batch_size=128, CFG=CFG)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in ds.host_batches():
+        pass
+    barrier()
+    t_dec = time.perf_counter() - t0
+    t = torch.tensor(times + [t_dec], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cold, warm, t_dec = (float(v) for v in t.tolist())
+    os.environ.pop("VIP_DEVICE_BATCH", None)
+    res = None
+    if rank == 0:
+        res = {"workload": f"{n_images} synthetic 200x200 JPEG files ({unique} distinct), models {model_names}, tta {tta}, "
+                           f"{world} GPU(s), batch {device_batch or 128}",
+               "images": n_images, "wall_s_cold": cold, "wall_s_warm": warm,
+               "images_per_s_cold": n_images / cold, "images_per_s_warm": n_images / warm,
+               "host_decode_only_images_per_s": n_images / t_dec, "host_cores": os.cpu_count(),
+               "rows_written": int(len(df)), "labels_synthetic_fraction": float(df.logit.mean()),
+               "includes": "file read + libjpeg decode (thread pool), H2D, preprocess + forward graphs, D2H, "
+                           + ("NCCL all_gather, " if world > 1 else "") + "pandas epilogue, CSV write",
+               "limiter": "host JPEG decode" if n_images / t_dec < 1.5 * n_images / warm else "device"}
+        import shutil
+
+        shutil.rmtree(root, ignore_errors=True)
+    return res
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -243,8 +529,18 @@ def run_ours(args):
 
     # models (random-init: checkpoints are unavailable offline) and synthetic decoded images
     models = []
+    parity = world == 1 and not args.no_cpu_baseline   # checker leg: the step's own output against the CPU oracle
     for name, dim in MODELS:
-        models.append((registry.create_model(name, dim, num_classes=2, device=dev).init_random(seed=rank), dim))
+        m = registry.create_model(name, dim, num_classes=2, device=dev)
+        if parity:
+            # same seeded weights on both sides (the oracle's non-degenerate generator; inputs, not compute)
+            from oracle import gcvit as _G
+            from oracle import resnet_rs as _R
+
+            m.load_weights(_R.random_weights(101, 2, seed=0) if name.startswith("ResNetRS") else _G.random_weights("small", 2, seed=0))
+        else:
+            m.init_random(seed=rank)
+        models.append((m, dim))
     rng = np.random.default_rng(1234 + rank)
     base = rng.integers(0, 256, (64, HS, WS, 3), dtype=np.uint8)
     base = ((base.astype(np.uint16) + np.roll(base, 1, 2) + np.roll(base, 2, 2) + np.roll(base, 1, 1)) // 4).astype(np.uint8)
@@ -273,6 +569,9 @@ def run_ours(args):
     clocks = sampler.stop()
     total_ms = evs[0].elapsed_time(evs[1])
     finite = bool(torch.isfinite(pred.acc).all())
+    parity_err = None
+    if parity:
+        parity_err = parity_sample(pred, dev)
 
     # e2e through the host-buffer call: pinned host images in, probabilities out
     e2e_steps = max(2, min(args.steps, 10))
@@ -300,7 +599,9 @@ def run_ours(args):
                        "models": [m for m, _ in MODELS], "weights": "random-init (seeded)",
                        "l2": "activations per step (> 10 GB) far exceed the 126 MB L2",
                        "sharding": "images sharded across ranks, models replicated, no data-path collective",
-                       "finite_outputs": finite},
+                       "finite_outputs": finite, "parity_sample_max_err": parity_err,
+                       "parity_sample": "max |P_b200 - P_oracle| of the ensemble P(synthetic) over 16 oracle images placed in "
+                                        "the 1024-image step (fp32 CPU oracle, same weights); null when the CPU legs are off"},
             "clocks": clocks,
             "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "images/s",
                     "h2d_bytes_per_step": int(src_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps,
@@ -314,6 +615,9 @@ def run_ours(args):
                          "note": "achieved = algorithmic FLOPs of the step / CUDA-event step time (all kernels of the step, "
                                  "not only the GEMMs); per-kernel shares: profiles/"},
         }
+        if not args.no_extras:
+            line["preprocess_nojpeg"] = bench_preprocess_nojpeg(dev, max(5, min(args.steps, 20)), hbm_peak)
+            line["gcvit_tiny_b256"] = bench_gcvit_tiny_b256(dev, max(5, min(args.steps, 20)), tc_peak)
         if not args.no_preprocess_only:
             pre_ms = bench_preprocess_only(dev, max(5, min(args.steps, 20)))
             ach = PRE_BYTES_PER_IMAGE * PRE_N / (pre_ms * 1e-3) / 1e9
@@ -327,7 +631,21 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, sample = cpu_baseline(cores)
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "config0": cpu_baseline_config0(cores)}
+    main_py = {}
+    if not args.no_main_py:
+        # every rank takes part (sharded list, all_gather of the result); rank 0 keeps the numbers
+        del pred
+        torch.cuda.empty_cache()
+        if world == 1:
+            main_py["main_py_config0"] = bench_main_py("c0", 64, 64, ["ResNetRS50-200x200"], 1, rank, world, local_rank, dist,
+                                                       device_batch=16)
+        main_py["main_py_config4"] = bench_main_py("c4", 5000, 500, ["ResNetRS101-200x200", "GCViTSmall-224x224",
+                                                                     "ResNetRS50-200x200"], 2, rank, world, local_rank, dist,
+                                                   device_batch=512)
+    if rank == 0:
+        line.update(main_py)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -343,6 +661,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preprocess-only", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip preprocess_nojpeg and gcvit_tiny_b256")
+    ap.add_argument("--no-main-py", action="store_true", help="skip the predict_soln runs on JPEG files (configs[0], [4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant,head,seed", [("tiny", "softmax", 1), ("small", "sigmoid", 1), ("small", "softmax", 3),
+@pytest.mark.parametrize("variant,head,seed", [("tiny", "softmax", 3), ("small", "sigmoid", 5), ("small", "softmax", 3),
                                                ("xxtiny", "softmax", 5)])
 def test_gcvit_matches_oracle(cuda_device, variant, head, seed):
     import torch

@@ -45,14 +45,16 @@ def centred(model_name, W, n_cal=16):
     return R.center_head(W, taps["feat"], head_kernel="head/kernel", head_bias="head/bias")
 
 
-def main(model_dir, names, num_classes=2, folds=1):
+def main(model_dir, names, num_classes=2, folds=1, calibrate=True):
     entries = []
     for mi, name in enumerate(names):
         hw = [int(v) for v in name.rsplit("-", 1)[1].split("x")]
         d = os.path.join(model_dir, name, "ckpt")
         os.makedirs(d, exist_ok=True)
         for f in range(folds):
-            W = centred(name, weights_for(name, num_classes, seed=100 * mi + f))
+            W = weights_for(name, num_classes, seed=100 * mi + f)
+            if calibrate:
+                W = centred(name, W)
             np.savez(os.path.join(d, f"fold{f}.npz"), __num_classes__=np.int64(num_classes),
                      __head_act__=np.array("softmax" if num_classes > 1 else "sigmoid"), **W)
         entries.append([name, hw, 0])

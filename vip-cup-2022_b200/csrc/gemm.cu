@@ -311,7 +311,7 @@ enum EpiMode : int { EPI_GENERIC = 0, EPI_NONE, EPI_RELU, EPI_GELU, EPI_LN, EPI_
 template <int MODE>
 __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
                                           int N, float rstd, float nmr, const float* __restrict__ colsum,
-                                          const float* __restrict__ bias, float& rs_sum, float& rs_sq,
+                                          const float* __restrict__ bias, long long& rs_sum, long long& rs_sq,
                                           const float* __restrict__ gate_row = nullptr, float pivot = 0.0f,
                                           const __nv_bfloat16* __restrict__ lo_in = nullptr,
                                           __nv_bfloat16* __restrict__ lo_out = nullptr) {
@@ -368,12 +368,18 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
           v[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u);
         }
       }
+      // row statistics: an fp32 partial over these 8 columns (fixed order), then exact integer accumulation -- the
+      // 8-column groups are the same whatever tile width / epilogue grouping the launch picked, so the totals do not
+      // depend on the batch size either
+      float ps = 0.0f, pq = 0.0f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float d = v[i] - pivot;
-        rs_sum += d;
-        rs_sq = fmaf(d, d, rs_sq);
+        ps += d;
+        pq = fmaf(d, d, pq);
       }
+      rs_sum += to_fx(ps);
+      rs_sq += to_fx(pq);
     }
     uint32_t w[4];
 #pragma unroll
@@ -400,7 +406,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
                                               int N, int row, int M, const GemmEpilogue& e, bool has_res, float rstd,
                                               float nmr, const float* __restrict__ p_colsum,
                                               const float* __restrict__ p_bias, const float* __restrict__ p_colscale,
-                                              float& rs_sum, float& rs_sq, float pivot) {
+                                              long long& rs_sum, long long& rs_sq, float pivot) {
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
     const int n = nb + q8 * 8;
@@ -426,14 +432,17 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
     }
     if (e.out_bf16 != nullptr) {
       uint32_t w[4];
+      float ps = 0.0f, pq = 0.0f;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
         w[t] = *reinterpret_cast<const uint32_t*>(&h2);
         const float lo = __uint_as_float(w[t] << 16) - pivot, hi = __uint_as_float(w[t] & 0xffff0000u) - pivot;
-        rs_sum += lo + hi;
-        rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
+        ps += lo + hi;
+        pq = fmaf(lo, lo, fmaf(hi, hi, pq));
       }
+      rs_sum += to_fx(ps);
+      rs_sq += to_fx(pq);
       *cp = make_uint4(w[0], w[1], w[2], w[3]);
     } else if (row < M) {
       float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
@@ -726,7 +735,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (!has_res) group_sync();   // (with a residual the wait on its arrival below orders the buffer reuse)
 
-      float rs_sum = 0.0f, rs_sq = 0.0f;
+      long long rs_sum = 0, rs_sq = 0;   // fixed point (stats.cuh)
       // chunks of this group; the warp's last TMEM read of the tile hands the accumulator stage back to the MMA warp
       const int j_first = kShared ? 0 : group * kCPG;
       const int j_last = min(kShared ? 0 : group * kCPG + kCPG - 1, nvalid - 1);
@@ -803,7 +812,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint8_t* cbase = cbuf + (bset + (uint32_t)j) * kCBufBytes;
           const int n = n0 + j * 64 + cpair * 2;
           if (n >= g.N) continue;
-          float s0 = 0.0f, s1 = 0.0f;
+          long long s0 = 0, s1 = 0;   // exact: every bf16 element is converted to fixed point before it is added
           if (g.conv == 2) {
             // patch tile: row rr = ((image, patch row, patch column)); rows outside the map / batch are skipped
             const int per_img = g.bw * g.bh;
@@ -816,20 +825,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (pn0 + ni >= g.Nimg || pp0 + py >= g.Ho || pq0 + px >= g.Wo) continue;
               if (ni != cur) {
                 if (cur >= 0) {
-                  fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
-                  fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+                  fx_atomic_add_raw(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+                  fx_atomic_add_raw(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
                 }
-                s0 = s1 = 0.0f;
+                s0 = s1 = 0;
                 cur = ni;
               }
               const uint32_t w = *reinterpret_cast<const uint32_t*>(
                   cbase + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) + (cpair & 3) * 4);
-              s0 += __uint_as_float(w << 16);
-              s1 += __uint_as_float(w & 0xffff0000u);
+              s0 += to_fx(__uint_as_float(w << 16));
+              s1 += to_fx(__uint_as_float(w & 0xffff0000u));
             }
             if (cur >= 0) {
-              fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
-              fx_atomic_add(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
+              fx_atomic_add_raw(e.gap + (size_t)(pn0 + cur) * g.N + n, s0);
+              fx_atomic_add_raw(e.gap + (size_t)(pn0 + cur) * g.N + n + 1, s1);
             }
           } else if (m0 + rq * kGapRows < g.M) {
             int rr = rq * kGapRows;
@@ -838,27 +847,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int k = 0; k < kGapRows; ++k, ++rr) {
               if (m0 + rr >= g.M) break;
               if (rr == next) {
-                fx_atomic_add(e.gap + (size_t)img * g.N + n, s0);
-                fx_atomic_add(e.gap + (size_t)img * g.N + n + 1, s1);
-                s0 = s1 = 0.0f;
+                fx_atomic_add_raw(e.gap + (size_t)img * g.N + n, s0);
+                fx_atomic_add_raw(e.gap + (size_t)img * g.N + n + 1, s1);
+                s0 = s1 = 0;
                 ++img;
                 next += e.gap_rows;
               }
               const uint32_t w = *reinterpret_cast<const uint32_t*>(
                   cbase + rr * 128 + ((((uint32_t)(cpair >> 2)) ^ (uint32_t)(rr & 7)) << 4) + (cpair & 3) * 4);
-              s0 += __uint_as_float(w << 16);
-              s1 += __uint_as_float(w & 0xffff0000u);
+              s0 += to_fx(__uint_as_float(w << 16));
+              s1 += to_fx(__uint_as_float(w & 0xffff0000u));
             }
-            fx_atomic_add(e.gap + (size_t)img * g.N + n, s0);
-            fx_atomic_add(e.gap + (size_t)img * g.N + n + 1, s1);
+            fx_atomic_add_raw(e.gap + (size_t)img * g.N + n, s0);
+            fx_atomic_add_raw(e.gap + (size_t)img * g.N + n + 1, s1);
           }
         }
       }
       if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 6] = clock64();
       if (e.row_stats != nullptr && row < g.M && j_last >= j_first) {
         long long* rec = e.row_stats + 3 * (size_t)row;
-        fx_atomic_add(rec, rs_sum);
-        fx_atomic_add(rec + 1, rs_sq);
+        fx_atomic_add_raw(rec, rs_sum);
+        fx_atomic_add_raw(rec + 1, rs_sq);
         if (n0 == 0 && group == 0) rec[2] = (long long)__float_as_int(pivot);   // the thread that holds column 0
       }
     }

@@ -7,7 +7,7 @@
 //   grid   = (stripes of kRows output rows, images): >= 12 waves of small CTAs at batch 1024
 //   stage  : the source rows a stripe touches are one contiguous byte range of the image -> 16-byte loads into smem
 //   warp   = one output row at a time: vertical taps of the row (4 source bytes per lane and step -> packed fp32 pairs,
-//            mul.rn.f32x2 / add.rn.f32x2: separately rounded like TF's un-contracted CPU kernel, half the issue slots)
+//            separately rounded packed products and sums like TF's un-contracted CPU kernel, half the issue slots)
 //            -> the warp's fp32 row buffer -> horizontal taps, / 255, gray, one lane per pixel -> the warp's output row
 //            buffer (flips applied as addressing) -> 16-byte coalesced streaming stores
 //   tables : tap weights / indices depend only on (Hs, Ws, Ho, Wo): computed once per geometry by tap_table_kernel into
@@ -45,18 +45,12 @@ struct StreamArgs {
   int identity;
   int off_ix, off_src, off_v, off_o;   // smem byte offsets (wx first)
   int v_stride, o_stride;              // bytes per warp buffer
+  float one;                           // 1.0f, opaque to the compiler (see tap4x2)
 };
 
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   float2 d;
   asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nadd.rn.f32x2 rd, ra, rb;\nmov.b64 {%0,%1}, rd;\n}"
       : "=f"(d.x), "=f"(d.y)
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
@@ -70,10 +64,13 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return d;
 }
 // tap4 (resize_math.cuh) on two independent values: ((p0 w0 + p1 w1) + p2 w2) + p3 w3, every product and sum rounded
-__device__ __forceinline__ float2 tap4x2(float2 p0, float2 p1, float2 p2, float2 p3, const float4 w) {
+// separately.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (also with -fmad=false), which would round
+// once where TF rounds twice; so the sums are written as fma(x, one, y) with `one` = 1.0f read from the kernel arguments:
+// exact (x * 1 + y rounds like x + y), packed, and not foldable at compile time.
+__device__ __forceinline__ float2 tap4x2(float2 p0, float2 p1, float2 p2, float2 p3, const float4 w, const float2 one) {
   const float2 a = mul2(p0, make_float2(w.x, w.x)), b = mul2(p1, make_float2(w.y, w.y));
   const float2 c = mul2(p2, make_float2(w.z, w.z)), d = mul2(p3, make_float2(w.w, w.w));
-  return add2(add2(add2(a, b), c), d);
+  return fma2(fma2(fma2(a, one, b), one, c), one, d);
 }
 // div255 (resize_math.cuh) on a pair
 __device__ __forceinline__ float2 div255x2(float2 x) {
@@ -170,6 +167,7 @@ __global__ void __launch_bounds__(kThreads, 3) resize_stream_kernel(const Stream
   __syncthreads();
 
   const int nwords = a.pitch >> 2;
+  const float2 one = make_float2(a.one, a.one);
   for (int r = warp; r < rows; r += kWarps) {
     const int oy = oy0 + r;
     const float4 wy = __ldg(a.wy + oy);
@@ -182,9 +180,9 @@ __global__ void __launch_bounds__(kThreads, 3) resize_stream_kernel(const Stream
     for (int j = lane; j < nwords; j += 32) {
       const unsigned A = t0[j], B = t1[j], C = t2[j], D = t3[j];
       const float2 v01 = tap4x2(make_float2(u8f(A, 0), u8f(A, 1)), make_float2(u8f(B, 0), u8f(B, 1)),
-                                make_float2(u8f(C, 0), u8f(C, 1)), make_float2(u8f(D, 0), u8f(D, 1)), wy);
+                                make_float2(u8f(C, 0), u8f(C, 1)), make_float2(u8f(D, 0), u8f(D, 1)), wy, one);
       const float2 v23 = tap4x2(make_float2(u8f(A, 2), u8f(A, 3)), make_float2(u8f(B, 2), u8f(B, 3)),
-                                make_float2(u8f(C, 2), u8f(C, 3)), make_float2(u8f(D, 2), u8f(D, 3)), wy);
+                                make_float2(u8f(C, 2), u8f(C, 3)), make_float2(u8f(D, 2), u8f(D, 3)), wy, one);
       reinterpret_cast<float4*>(s_v)[j] = make_float4(v01.x, v01.y, v23.x, v23.y);
     }
     __syncwarp();
@@ -197,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 3) resize_stream_kernel(const Stream
       const float* p2 = s_v + 3 * ix.z;
       const float* p3 = s_v + 3 * ix.w;
       const float2 rg = div255x2(tap4x2(make_float2(p0[0], p0[1]), make_float2(p1[0], p1[1]), make_float2(p2[0], p2[1]),
-                                        make_float2(p3[0], p3[1]), wx));
+                                        make_float2(p3[0], p3[1]), wx, one));
       const float bl = div255(tap4(p0[2], p1[2], p2[2], p3[2], wx));
       float px[3] = {rg.x, rg.y, bl};
       if (flags & VIP_FLAG_GRAY) gray3(px);
@@ -278,6 +276,7 @@ int preprocess_stream(const uint8_t* src, int N, int Hs, int Ws, const uint8_t* 
   a.N = N; a.Hs = Hs; a.Ws = Ws; a.Ho = Ho; a.Wo = Wo;
   a.pitch = Ws * 3;
   a.identity = (Hs == Ho && Ws == Wo) ? 1 : 0;
+  a.one = 1.0f;
   TapTables t;
   int rc = get_tables(Hs, Ws, Ho, Wo, st, &t);
   if (rc != VIP_OK) return rc;

@@ -1,9 +1,11 @@
 // Order-independent accumulators for the statistics that cross kernels (LayerNorm row statistics, pooled sums).
 //
-// Partial sums are produced by many threads / CTAs whose order of arrival is not fixed.  fp32 atomics would make the
-// result depend on that order (and with it every logit downstream), so each thread's partial sum -- computed in a fixed
-// order -- is converted to 36.28 fixed point and added with 64-bit INTEGER atomics: integer addition is associative, the
-// total is bit-reproducible from run to run and independent of the tile schedule / batch size.
+// Partial sums are produced by many threads / CTAs whose order of arrival is not fixed, and which thread sums which
+// elements depends on the tile configuration a launch picks (i.e. on the batch size).  fp32 atomics would make the
+// result depend on both (and with it every logit downstream).  So values are converted to 36.28 fixed point EARLY --
+// pooled sums element by element, row statistics per aligned group of 8 columns -- and everything after that is 64-bit
+// INTEGER addition (registers, then atomics): associative, hence bit-reproducible from run to run and independent of the
+// tile schedule, the tile shape and the batch an image is in.
 //
 // Row statistics record (3 x int64 per row): { sum (v - p), sum (v - p)^2, bits of the pivot p }.  The pivot (the row's
 // previous value of column 0, i.e. something close to the row mean) keeps the one-pass variance
@@ -22,6 +24,10 @@ __device__ __forceinline__ long long to_fx(float v) { return __float2ll_rn(v * k
 __device__ __forceinline__ float from_fx(long long v) { return __ll2float_rn(v) * kFxInv; }
 __device__ __forceinline__ void fx_atomic_add(long long* p, float v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(to_fx(v)));
+}
+
+__device__ __forceinline__ void fx_atomic_add_raw(long long* p, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
 }
 
 struct RowMoments {
