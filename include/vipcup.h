@@ -92,22 +92,26 @@ int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, 
 /* Epilogue description of vip_gemm_bf16_ex / vip_conv2d_bf16, applied per output element (m, n) in this order:
  *   v = acc
  *   v = rstd[m] * (v - mean[m] * ln_colsum[n])   if ln_stats: LayerNormalization of the A rows folded into the contraction
- *        (models/gcvit/layers/block.py:28,39 feeding attention.py:25 / feature.py:20): (mean, rstd) come from the row
- *        statistics record ln_stats[m] over ln_cols columns; B must hold gamma-scaled weights, bias must hold beta @ W + b
+ *        (models/gcvit/layers/block.py:28,39 feeding attention.py:25 / feature.py:20): ln_stats[m] = (mean, rstd) of row m,
+ *        written by vip_row_stats_finalize / vip_layernorm_bf16 / vip_mlp_fused_bf16; B must hold gamma-scaled weights,
+ *        bias must hold beta @ W + b
  *   v += bias[n];  v = act(v);  v *= colscale[n];  v += residual[m, n];  store as bf16 or f32
- *   row_stats[m] += (sum_n (out - p), sum_n (out - p)^2, p)   if row_stats: a row statistics record (below) that feeds the
- *        ln_stats of the next contraction
+ *   row_stats[m] += (sum_n (out - p), sum_n (out - p)^2, p)   if row_stats: a row statistics record (below);
+ *        vip_row_stats_finalize turns the records into the ln_stats of the next contraction
  *   gap[m / gap_rows, n] += out                   if gap: GlobalAveragePooling2D partial sums (SE squeeze,
  *        models/resnet_rs/resnet_rs_model.py:149), 36.28 fixed point
  * Statistics that cross kernels are accumulated with 64-bit INTEGER atomics on fixed-point values (value * 2^28), so the
  * totals do not depend on the order in which tiles finish: outputs are bit-reproducible and independent of the batch an
  * image is in.  A row statistics record is int64[3] = { sum (v - p), sum (v - p)^2 (both fixed point), bits of the f32
- * pivot p }; p is the row's previous column-0 value (0 without a residual), which keeps the one-pass variance free of
- * cancellation when |mean| >> sigma.
- * Two-plane residual stream (residual_lo / out_lo, both bf16 with the leading dimensions of residual / out): the running
- * sum x of a pre-LN transformer block (models/gcvit/layers/block.py:77-81) is carried as hi + lo; v = acc + bias + hi + lo,
- * out = bf16(v), out_lo = bf16(v - out).  The hi plane is the A operand of the next contraction; needs a residual, a bf16
- * output and a bias-only epilogue.  residual_lo may be NULL (zeros) with out_lo set.
+ * pivot p }; p comes from row_pivot (the mean the previous LayerNorm computed for the residual row; 0 when absent), which
+ * keeps the one-pass variance free of cancellation when |mean| >> sigma.
+ * Two-plane residual stream (residual_lo / out_lo, bf16): the running sum x of a pre-LN transformer block
+ * (models/gcvit/layers/block.py:77-81) is carried as hi + lo; v = acc + bias + hi + lo, out = bf16(v), out_lo = bf16(v - out).
+ * The hi plane is the A operand of the next contraction; needs a residual, a bf16 output and a bias-only epilogue.
+ * residual_lo may be NULL (zeros) with out_lo set.  A low plane is an opaque buffer of ceil(M / 32) * 32 * N bf16 elements
+ * that only these epilogues read and write, stored in blocks of 32 rows x 8 columns (512 contiguous bytes, row-major inside):
+ * element (m, n) lies at ((m / 32) * (N / 8) + n / 8) * 256 + (m % 32) * 8 + n % 8 -- the order in which the epilogue
+ * warps (one thread per row) touch it, so that their 16-byte accesses coalesce.
  * With row_gate the order is that of an SE bottleneck tail (resnet_rs_model.py:183,278-280):
  *   v = relu((acc + bias[n]) * row_gate[m / gate_rows, n] + residual[m, n])   (needs residual, act relu, bf16 output)
  * row_stats and gap are accumulated: the caller zeroes them (vip_memset_async). */
@@ -120,17 +124,17 @@ typedef struct vip_epilogue {
   void* out;              /* bf16 or f32 [M, ldc] */
   int ldc;
   int out_dtype;          /* VIP_DTYPE_* */
-  const int64_t* ln_stats; /* [M, 3] row statistics records or NULL */
+  const float* ln_stats;  /* [M, 2] (mean, 1 / sigma) of the A rows, or NULL */
   const float* ln_colsum; /* [N] */
-  int ln_cols;
-  float ln_eps;
   int64_t* row_stats;     /* [M, 3] row statistics records or NULL */
   int64_t* gap;           /* [ceil(M / gap_rows), N] fixed point or NULL */
   int gap_rows;
   const float* row_gate;  /* f32 [ceil(M / gate_rows), N] or NULL: squeeze-excite gate of the image a row belongs to */
   int gate_rows;
-  const void* residual_lo; /* bf16 [M, ldr] or NULL: low plane of the residual */
-  void* out_lo;            /* bf16 [M, ldc] or NULL: low plane of the output */
+  const void* residual_lo; /* low plane of the residual (blocked layout) or NULL */
+  void* out_lo;            /* low plane of the output (blocked layout) or NULL */
+  const float* row_pivot;  /* f32 [M, 2] or NULL: [m][0] = pivot p of row m's statistics record -- pass the ln_stats of the
+                              LayerNorm that last read the residual row (its mean is close to the new row's mean) */
 } vip_epilogue_t;
 
 /* vip_gemm_bf16 with the full epilogue. N, K, lda, ldb, ldc, ldr multiples of 8. */
@@ -158,10 +162,13 @@ int vip_global_avgpool_bf16(const void* x, int N, int HW, int C, void* out_bf16,
  * SE excite + Add + ReLU, resnet_rs_model.py:183,278-280; gcvit feature.py:66,109,150 */
 int vip_scale_add_act_bf16(const void* y, const float* gate, const void* shortcut, void* out, int N, int HW, int C, int act,
                            void* cuda_stream);
-/* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79.  row_stats
- * (int64 [M,3] or NULL) receives the row statistics record (see vip_epilogue_t) of every OUTPUT row, the ln_stats of a
- * LayerNorm folded into the next contraction. */
-int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, int64_t* row_stats, long long M,
+/* Row statistics records (int64 [M,3], see vip_epilogue_t) -> out f32 [M,2] = (mean, 1 / sqrt(var + eps)) over `cols`
+ * columns: the ln_stats operand of a contraction with a folded LayerNormalization. */
+int vip_row_stats_finalize(const int64_t* records, long long M, int cols, float eps, float* out, void* cuda_stream);
+/* LayerNormalization(axis=-1, epsilon) over [M,C]: gcvit block.py:28,39; feature.py:100-101; gcvit.py:79.  ln_next
+ * (f32 [M,2] or NULL) receives (mean, 1 / sqrt(var + next_eps)) of every (rounded) OUTPUT row: the ln_stats of a LayerNorm
+ * folded into the next contraction. */
+int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* ln_next, float next_eps, long long M,
                        int C, float eps, void* cuda_stream);
 /* ZeroPadding2D(1) + DepthwiseConv2D(3,'valid',no bias) (+ GELU if gelu != 0); w f32 [3,3,C]: gcvit feature.py:92-94,132-134.
  * gap (int64 [N,C] fixed point or NULL, zeroed by the caller) accumulates the per-image channel sums of the output: the
@@ -176,6 +183,11 @@ int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, vo
  * attention.py:39-50; out bf16 [B*H*W, C].  ws 7 and 14 are built. */
 int vip_window_attention_bf16(const void* qkv, const void* q_global, const float* rel_table, void* out, int B, int H, int W,
                               int C, int ws, int heads, void* cuda_stream);
+/* FitWindow padding and the crop after a level's blocks (gcvit feature.py:234-256, level.py:49,61):
+ * out[n, y, x, :] = x[n, y - top, x - left, :] where that source pixel exists, zero elsewhere; x is [N,H,W,bytes_per_pixel]
+ * (bytes_per_pixel % 8 == 0: bf16 activations with C % 4 == 0, or int64[3] row statistics records), out [N,Ho,Wo,...]. */
+int vip_pad_crop(const void* x, int N, int H, int W, int bytes_per_pixel, void* out, int Ho, int Wo, int top, int left,
+                 void* cuda_stream);
 /* Classifier head on pooled f32 features [N,C]: Dense(k) (w f32 [C,k], b [k]) + softmax (sigmoid_head = 0) or sigmoid,
  * probs f32 [N,k]; when acc != NULL also acc[n] += acc_weight * P(synthetic) with P = k > 1 ? 1 - probs[n,0] : probs[n,0]
  * (TTA / fold / ensemble means of main.py:110-121,142 as one fused accumulation): resnet_rs_model.py:474-476, gcvit.py:88 */
@@ -192,15 +204,15 @@ int vip_gemm_grouped_bf16(const void* A, int lda, const void* B, int ldb, int M,
 int vip_scale_weights_bf16(const void* w, int ldw, const float* gate, int G, int N, int K, void* out, void* cuda_stream);
 /* Fused pre-LN MLP of a GCViT block (models/gcvit/layers/block.py:39-56,77-81; layers/feature.py:8-43):
  *   out[m, :] = x[m, :] + W2 gelu(W1 LayerNorm(x[m, :]) + b1) + b2     with LayerNorm folded like vip_epilogue_t.ln_stats:
- *   ln_stats int64 [M, 3] = row statistics records of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,
+ *   ln_stats f32 [M, 2] = (mean, 1 / sigma) of the rows of x, w1 bf16 [hidden, ldw1] holds gamma-scaled weights,
  *   colsum1 [hidden] their column sums, bias1 [hidden] = beta W1 + b1; w2 bf16 [C, ldw2], bias2 [C] (layer scale folded).
- *   x, out bf16 [M, C] contiguous; row_stats int64 [M, 3] (or NULL) receives the records of the rows of out; x_lo /
- *   out_lo (bf16 [M, C] or NULL): low planes of the two-plane residual stream (see vip_epilogue_t).
+ *   x, out bf16 [M, C] contiguous; ln_next f32 [M, 2] (or NULL) receives (mean, 1 / sqrt(var + next_eps)) of the rows of
+ *   out; x_lo / out_lo (or NULL): low planes of the two-plane residual stream (see vip_epilogue_t).
  * The hidden activations stay in TMEM / shared memory.  Built for (C, hidden) = (96, 192) and (64, 192); any other shape
  * returns VIP_ERR_UNSUPPORTED and the caller issues two vip_gemm_bf16_ex calls instead. */
-int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int hidden, const int64_t* ln_stats, float ln_eps,
+int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int hidden, const float* ln_stats, float next_eps,
                        const void* w1, int ldw1, const float* colsum1, const float* bias1, const void* w2, int ldw2,
-                       const float* bias2, void* out, void* out_lo, int64_t* row_stats, void* cuda_stream);
+                       const float* bias2, void* out, void* out_lo, float* ln_next, void* cuda_stream);
 /* out = bf16(x * 2^-28 * scale): fixed-point pooled sums of the fused gap epilogue -> means (SE squeeze,
  * resnet_rs_model.py:149) */
 int vip_scale_cast_fx_bf16(const int64_t* x, float scale, void* out, long long n, void* cuda_stream);

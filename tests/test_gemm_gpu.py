@@ -15,16 +15,12 @@ def decode_stats(rec, cols):
     return piv + d, rec[:, 1].double() * FX / cols - d * d
 
 
-def encode_stats(x):
-    """Row statistics records of the rows of x (pivot = column 0), as a producer kernel would emit them."""
+def moments(x, eps=1e-5):
+    """f32 [M, 2] (mean, 1 / sigma) of the rows of x: the ln_stats operand of a folded LayerNorm."""
     import torch
 
     xf = x.double()
-    p = xf[:, :1]
-    s1 = torch.round((xf - p).sum(1) / FX).to(torch.int64)
-    s2 = torch.round(((xf - p) ** 2).sum(1) / FX).to(torch.int64)
-    pv = x[:, 0].float().contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
-    return torch.stack([s1, s2, pv], 1).contiguous()
+    return torch.stack([xf.mean(1), 1.0 / torch.sqrt(xf.var(1, unbiased=False) + eps)], 1).float().contiguous()
 
 
 @pytest.mark.parametrize("m,n,k", [
@@ -90,7 +86,10 @@ def test_gemm_folded_layernorm_and_row_stats(cuda_device, m, n, k):
     wg = (wt * gamma[None, :]).to(torch.bfloat16)
     colsum = wg.float().sum(1).contiguous()
     b2 = (wt @ beta + bias).contiguous()
-    out = nn.gemm(x, wg, bias=b2, act="gelu", ln_stats=stats, ln_colsum=colsum, ln_cols=k, ln_eps=1e-5)
+    ln = nn.finalize_stats(stats, k, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.allclose(ln, moments(xs), rtol=1e-4, atol=1e-5)
+    out = nn.gemm(x, wg, bias=b2, act="gelu", ln_stats=ln, ln_colsum=colsum)
     ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(xs, (k,), gamma, beta, 1e-5) @ wt.t() + bias)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
@@ -170,16 +169,13 @@ def test_layernorm_matches_torch(cuda_device, m, c):
     x = (torch.randn((m, c), generator=g) * 2.0 + 0.5).to(torch.bfloat16).to(cuda_device)
     gamma = (torch.rand((c,), generator=g) + 0.5).to(cuda_device)
     beta = (torch.randn((c,), generator=g) * 0.3).to(cuda_device)
-    stats = nn.row_stats_buffer(m, device=cuda_device)
-    got = nn.layernorm(x, gamma, beta, eps=1e-5, row_stats=stats)
+    stats = torch.empty((m, 2), dtype=torch.float32, device=cuda_device)
+    got = nn.layernorm(x, gamma, beta, eps=1e-5, ln_next=stats, next_eps=1e-5)
     ref = torch.nn.functional.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
     torch.cuda.synchronize()
     err = (got.float() - ref).abs()
     assert (err <= ref.abs() * 2.0 ** -8 + 1e-3).all(), err.max().item()
-    gf = got.double()
-    mean, var = decode_stats(stats, c)
-    assert torch.allclose(mean, gf.mean(1), rtol=1e-5, atol=1e-5)
-    assert torch.allclose(var, gf.var(1, unbiased=False), rtol=1e-4, atol=1e-6)
+    assert torch.allclose(stats, moments(got), rtol=1e-4, atol=1e-5)      # of the ROUNDED output rows
 
 
 @pytest.mark.parametrize("m,c,hidden", [(128, 96, 192), (1000, 96, 192), (40000, 96, 192), (777, 64, 192), (128 * 149 + 5, 64, 192)])
@@ -205,23 +201,25 @@ def test_mlp_fused_matches_two_gemms_and_torch(cuda_device, m, c, hidden):
     w2 = k2.T.contiguous().to(torch.bfloat16).to(cuda_device)               # [c, hidden]
     bias2 = b2.to(cuda_device)
     xf = x.float()
-    stats = encode_stats(x)
-    x_lo = (torch.randn((m, c), generator=g) * 2.0 ** -9).to(torch.bfloat16).to(cuda_device)   # low plane of the stream
-    rs_f = nn.row_stats_buffer(m, device=cuda_device)
-    got, got_lo = nn.mlp_fused(x, stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=rs_f, x_lo=x_lo, want_lo=True)
-    hdn = nn.gemm(x, w1, bias=bias1, act="gelu", ln_stats=stats, ln_colsum=colsum1, ln_cols=c, ln_eps=1e-5)
+    stats = moments(x)
+    x_lo_rows = (torch.randn((m, c), generator=g) * 2.0 ** -9).to(torch.bfloat16).to(cuda_device)   # low plane of the stream
+    x_lo = nn.lo_plane_from_rows(x_lo_rows)
+    ln_f = torch.empty((m, 2), dtype=torch.float32, device=cuda_device)
+    got, got_lo = nn.mlp_fused(x, stats, w1, colsum1, bias1, w2, bias2, next_eps=1e-5, ln_next=ln_f, x_lo=x_lo, want_lo=True)
+    hdn = nn.gemm(x, w1, bias=bias1, act="gelu", ln_stats=stats, ln_colsum=colsum1)
     rs_g = nn.row_stats_buffer(m, device=cuda_device)
-    two_lo = torch.empty_like(x)
+    two_lo = nn.lo_plane(m, c, cuda_device)
     two = nn.gemm(hdn, w2, bias=bias2, residual=x, row_stats=rs_g, residual_lo=x_lo, out_lo=two_lo)
     torch.cuda.synchronize()
+    got_lo, two_lo = nn.lo_plane_to_rows(got_lo, m), nn.lo_plane_to_rows(two_lo, m)
     d = (got.float() - two.float()).abs()
     assert (d <= two.float().abs() * 2.0 ** -7 + 1e-3).all(), d.max().item()
     d2 = ((got.float() + got_lo.float()) - (two.float() + two_lo.float())).abs()     # the two-plane sums agree much closer
     assert (d2 <= two.float().abs() * 2.0 ** -7 + 1e-3).all(), d2.max().item()
-    (mf, vf), (mg, vg) = decode_stats(rs_f, c), decode_stats(rs_g, c)
-    assert torch.allclose(mf, mg, rtol=2e-3, atol=2e-3) and torch.allclose(vf, vg, rtol=5e-3, atol=1e-3)
-    full = got.double() + got_lo.double()
-    assert torch.allclose(mf, full.mean(1), rtol=1e-4, atol=1e-4) and torch.allclose(vf, full.var(1, unbiased=False), rtol=1e-3, atol=1e-5)
+    ln_g = nn.finalize_stats(rs_g, c, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.allclose(ln_f, ln_g, rtol=5e-3, atol=2e-3)
+    assert torch.allclose(ln_f, moments(got.double() + got_lo.double()), rtol=1e-3, atol=1e-4)
     ln = torch.nn.functional.layer_norm(xf.cpu(), (c,), gamma, beta, 1e-5)
     ref = xf.cpu() + torch.nn.functional.gelu(ln @ k1 + b1) @ k2 + b2
     assert (got.float().cpu() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
@@ -267,12 +265,15 @@ def test_gemm_two_plane_residual_stream(cuda_device, m, n, k):
     hi = res.to(torch.bfloat16)
     lo = (res - hi.float()).to(torch.bfloat16)
     hi, lo = hi.to(cuda_device), lo.to(cuda_device)
+    lo_blk = nn.lo_plane_from_rows(lo)
+    assert torch.equal(nn.lo_plane_to_rows(lo_blk, m), lo)
     outs = []
     for _ in range(2):
         st = nn.row_stats_buffer(m, device=cuda_device)
-        out_lo = torch.empty((m, n), dtype=torch.bfloat16, device=cuda_device)
-        out = nn.gemm(a, w, bias=bias, residual=hi, residual_lo=lo, out_lo=out_lo, row_stats=st)
-        outs.append((out, out_lo, st))
+        out_lo = nn.lo_plane(m, n, cuda_device)
+        out = nn.gemm(a, w, bias=bias, residual=hi, residual_lo=lo_blk, out_lo=out_lo, row_stats=st,
+                      row_pivot=moments(hi.float() + lo.float()))
+        outs.append((out, nn.lo_plane_to_rows(out_lo, m), st))
     torch.cuda.synchronize()
     for t0, t1 in zip(*outs):
         assert torch.equal(t0, t1)
@@ -287,10 +288,11 @@ def test_gemm_two_plane_residual_stream(cuda_device, m, n, k):
     assert torch.allclose(mean, ref.mean(1), rtol=1e-5, atol=1e-4)
     assert torch.allclose(var, ref.var(1, unbiased=False), rtol=1e-4, atol=1e-5)
     # first block of a level: no incoming low plane
-    out_lo2 = torch.empty_like(out_lo)
+    out_lo2 = nn.lo_plane(m, n, cuda_device)
     out2 = nn.gemm(a, w, bias=bias, residual=hi, out_lo=out_lo2)
     ref2 = a.double() @ w.double().t() + bias.double() + hi.double()
     torch.cuda.synchronize()
+    out_lo2 = nn.lo_plane_to_rows(out_lo2, m)
     assert ((out2.double() + out_lo2.double() - ref2).abs() <= ref2.abs() * 2.0 ** -15 + 1e-5).all()
 
 
@@ -312,9 +314,11 @@ def test_folded_layernorm_with_large_row_mean(cuda_device, c, n):
     a = (torch.randn(m, 64, generator=g) * 0.05).to(torch.bfloat16).to(cuda_device)
     w0 = (torch.randn(c, 64, generator=g) * 0.1).to(torch.bfloat16).to(cuda_device)
     st = nn.row_stats_buffer(m, device=cuda_device)
-    x_lo = torch.empty((m, c), dtype=torch.bfloat16, device=cuda_device)
-    x = nn.gemm(a, w0, residual=hi, residual_lo=lo, out_lo=x_lo, row_stats=st)
+    x_lo = nn.lo_plane(m, c, cuda_device)
+    x = nn.gemm(a, w0, residual=hi, residual_lo=nn.lo_plane_from_rows(lo), out_lo=x_lo, row_stats=st,
+                row_pivot=moments(hi.float() + lo.float()))     # as in a block: the moments the previous LayerNorm used
     torch.cuda.synchronize()
+    x_lo = nn.lo_plane_to_rows(x_lo, m)
     full = x.double() + x_lo.double()
     mean, var = decode_stats(st, c)
     assert torch.allclose(mean, full.mean(1), rtol=1e-6, atol=1e-5)
@@ -324,8 +328,8 @@ def test_folded_layernorm_with_large_row_mean(cuda_device, c, n):
     beta = (0.1 * torch.randn(c, generator=g)).to(cuda_device)
     wt = (torch.randn(n, c, generator=g) / c ** 0.5).to(cuda_device)
     wg = (wt * gamma[None, :]).to(torch.bfloat16)
-    out = nn.gemm(x, wg, bias=(wt @ beta).contiguous(), ln_stats=st, ln_colsum=wg.float().sum(1).contiguous(), ln_cols=c,
-                  ln_eps=1e-5, out_dtype=torch.float32)
+    out = nn.gemm(x, wg, bias=(wt @ beta).contiguous(), ln_stats=nn.finalize_stats(st, c, 1e-5),
+                  ln_colsum=wg.float().sum(1).contiguous(), out_dtype=torch.float32)
     # reference on the operand the kernel contracts (the hi plane) with the statistics of the full-precision stream
     mu, sd = full.mean(1, keepdim=True), (full.var(1, unbiased=False, keepdim=True) + 1e-5).sqrt()
     ref = ((x.double() - mu) / sd) @ wg.double().t() + (wt.double() @ beta.double())

@@ -19,9 +19,10 @@ class Epilogue(C.Structure):
     """vip_epilogue_t of include/vipcup.h"""
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("colscale", C.c_void_p), ("residual", C.c_void_p),
                 ("ldr", C.c_int), ("out", C.c_void_p), ("ldc", C.c_int), ("out_dtype", C.c_int),
-                ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
+                ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
                 ("row_stats", C.c_void_p), ("gap", C.c_void_p), ("gap_rows", C.c_int),
-                ("row_gate", C.c_void_p), ("gate_rows", C.c_int), ("residual_lo", C.c_void_p), ("out_lo", C.c_void_p)]
+                ("row_gate", C.c_void_p), ("gate_rows", C.c_int), ("residual_lo", C.c_void_p), ("out_lo", C.c_void_p),
+                ("row_pivot", C.c_void_p)]
 
 
 _lib = None
@@ -48,11 +49,13 @@ SIGNATURES = {
     "vip_global_avgpool_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vip_scale_add_act_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_void_p]),
-    "vip_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
-                                     C.c_float, C.c_void_p]),
+    "vip_layernorm_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_longlong,
+                                     C.c_int, C.c_float, C.c_void_p]),
+    "vip_row_stats_finalize": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "vip_dwconv3x3_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     "vip_maxpool3s2_bf16": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "vip_window_attention_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
+    "vip_pad_crop": (C.c_int, [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
     "vip_head_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_void_p]),
     "vip_scale_cast_fx_bf16": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]),

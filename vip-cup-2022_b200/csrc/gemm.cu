@@ -54,7 +54,9 @@ struct GemmArgs {
   // grouped B (plain GEMM only): rows [i * bgroup_mtiles * 128, ...) of A are contracted with rows
   // [i * bgroup_rows, (i + 1) * bgroup_rows) of B -- one weight matrix per image (0 = one B for all rows)
   int bgroup_mtiles, bgroup_rows;
-  int dbg;            // experiments: 4 = MMA warp does not wait for operands, 8 = MMA warp issues no MMAs
+  int dbg;            // experiments (VIP_GEMM_DEBUG): 4 = MMA warp does not wait for operands, 8 = MMA warp issues no MMAs,
+                      // 16 = folded-LN consumer does not load the statistics records, 32 = producer does not write its
+                      // records, 64 = low planes are not touched
   long long* trace;  // VIP_GEMM_TRACE=1: per-tile clock64() stamps of CTA 0 ([tile][8]); null otherwise
   GemmEpilogue epi;
 };
@@ -311,7 +313,7 @@ enum EpiMode : int { EPI_GENERIC = 0, EPI_NONE, EPI_RELU, EPI_GELU, EPI_LN, EPI_
 template <int MODE>
 __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow, uint32_t swz, uint32_t cbase16, int nb,
                                           int N, float rstd, float nmr, const float* __restrict__ colsum,
-                                          const float* __restrict__ bias, long long& rs_sum, long long& rs_sq,
+                                          const float* __restrict__ bias, float& rs_sum, float& rs_sq,
                                           const float* __restrict__ gate_row = nullptr, float pivot = 0.0f,
                                           const __nv_bfloat16* __restrict__ lo_in = nullptr,
                                           __nv_bfloat16* __restrict__ lo_out = nullptr) {
@@ -360,7 +362,7 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
         v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
       }
       if (lo_in != nullptr) {   // low plane of the two-plane residual stream (null for rows beyond M)
-        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo_in + n));
+        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo_in + (size_t)(n >> 3) * 256));
         const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -368,18 +370,14 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
           v[2 * t + 1] += __uint_as_float(wl[t] & 0xffff0000u);
         }
       }
-      // row statistics: an fp32 partial over these 8 columns (fixed order), then exact integer accumulation -- the
-      // 8-column groups are the same whatever tile width / epilogue grouping the launch picked, so the totals do not
-      // depend on the batch size either
-      float ps = 0.0f, pq = 0.0f;
+      // row statistics: fp32 partial sums over this 32-column piece, in column order (the caller converts them to fixed
+      // point once per piece)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float d = v[i] - pivot;
-        ps += d;
-        pq = fmaf(d, d, pq);
+        rs_sum += d;
+        rs_sq = fmaf(d, d, rs_sq);
       }
-      rs_sum += to_fx(ps);
-      rs_sq += to_fx(pq);
     }
     uint32_t w[4];
 #pragma unroll
@@ -396,7 +394,7 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
                                                         v[2 * t + 1] - __uint_as_float(w[t] & 0xffff0000u));
         wl[t] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      *reinterpret_cast<uint4*>(lo_out + n) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      *reinterpret_cast<uint4*>(lo_out + (size_t)(n >> 3) * 256) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
   }
 }
@@ -406,7 +404,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
                                               int N, int row, int M, const GemmEpilogue& e, bool has_res, float rstd,
                                               float nmr, const float* __restrict__ p_colsum,
                                               const float* __restrict__ p_bias, const float* __restrict__ p_colscale,
-                                              long long& rs_sum, long long& rs_sq, float pivot) {
+                                              float& rs_sum, float& rs_sq, float pivot) {
 #pragma unroll
   for (int q8 = 0; q8 < 4; ++q8) {
     const int n = nb + q8 * 8;
@@ -432,17 +430,14 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
     }
     if (e.out_bf16 != nullptr) {
       uint32_t w[4];
-      float ps = 0.0f, pq = 0.0f;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
         w[t] = *reinterpret_cast<const uint32_t*>(&h2);
         const float lo = __uint_as_float(w[t] << 16) - pivot, hi = __uint_as_float(w[t] & 0xffff0000u) - pivot;
-        ps += lo + hi;
-        pq = fmaf(lo, lo, fmaf(hi, hi, pq));
+        rs_sum += lo + hi;
+        rs_sq = fmaf(lo, lo, fmaf(hi, hi, rs_sq));
       }
-      rs_sum += to_fx(ps);
-      rs_sq += to_fx(pq);
       *cp = make_uint4(w[0], w[1], w[2], w[3]);
     } else if (row < M) {
       float4* op = reinterpret_cast<float4*>(e.out_f32 + (size_t)row * e.ldc + n);
@@ -670,14 +665,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
     uint32_t tcount = 0;  // tiles processed by this CTA; tile t stages into buffer set t % kSets
     // row statistics of the folded LayerNorm: fetched one tile ahead so that the load never sits on the critical path
-    struct StatRec { long long s1, s2, pv; };
-    auto load_stats = [&](int tile_) -> StatRec {
+    auto load_stats = [&](int tile_) -> float2 {   // (mean, 1 / sigma) of this thread's row of that tile
       const long long row_ = ((long long)(tile_ / g.n_tiles) * kCtas + cta_rank) * BM + rt;
-      if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return StatRec{0, 0, 0};
-      const long long* rec = e.ln_stats + 3 * row_;
-      return StatRec{__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
+      if (e.ln_stats == nullptr || tile_ >= total_tiles || row_ >= g.M || (g.dbg & 16)) return make_float2(0.0f, 1.0f);
+      return __ldg(reinterpret_cast<const float2*>(e.ln_stats) + row_);
     };
-    StatRec st_next = load_stats(cta_tile0);
+    float2 st_next = load_stats(cta_tile0);
+    auto load_pivot = [&](int tile_) -> float {
+      const long long row_ = ((long long)(tile_ / g.n_tiles) * kCtas + cta_rank) * BM + rt;
+      if (e.row_pivot == nullptr || e.row_stats == nullptr || tile_ >= total_tiles || row_ >= g.M) return 0.0f;
+      return __ldg(e.row_pivot + 2 * row_);
+    };
+    float pv_next = load_pivot(cta_tile0);
     for (int tile = cta_tile0; tile < total_tiles; tile += cta_tile_step, ++tcount) {
       const int m0 = ((tile / g.n_tiles) * kCtas + (int)cta_rank) * BM, n0 = (tile % g.n_tiles) * BN;
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -694,22 +693,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       float rstd = 1.0f, nmr = 0.0f;  // 1/sigma and -mean/sigma of this row (identity without a folded LayerNorm)
       if (e.ln_stats != nullptr) {
-        const StatRec st = st_next;
+        const float2 st = st_next;
         st_next = load_stats(tile + cta_tile_step);
-        const RowMoments mo = row_moments(st.s1, st.s2, st.pv, 1.0f / (float)e.ln_cols, e.ln_eps);
-        rstd = mo.rstd;
-        nmr = -mo.mean * mo.rstd;
+        rstd = st.y;
+        nmr = -st.x * st.y;
       }
       // two-plane residual stream: this row's low planes; pivot of the row statistics = the row's previous value of
       // column 0 (every thread of the row fetches the same two numbers, whichever N tile it works on)
       const bool row_ok = row < g.M;
-      const __nv_bfloat16* lo_in = (e.residual_lo != nullptr && row_ok) ? e.residual_lo + (size_t)row * e.ldr : nullptr;
-      __nv_bfloat16* lo_out = (e.out_lo != nullptr && row_ok) ? e.out_lo + (size_t)row * e.ldc : nullptr;
-      float pivot = 0.0f;
-      if (e.row_stats != nullptr && has_res && row_ok) {
-        pivot = __bfloat162float(e.residual[(size_t)row * e.ldr]);
-        if (lo_in != nullptr) pivot += __bfloat162float(lo_in[0]);
+      // (low planes are stored in 32-row x 8-column blocks, stats.cuh: lo_* point at this row's slot of column block 0,
+      //  column block k lies 256 elements further)
+      const __nv_bfloat16* lo_in = (e.residual_lo != nullptr && row_ok && !(g.dbg & 64)) ? e.residual_lo + lo_plane_index(row, 0, g.N) : nullptr;
+      __nv_bfloat16* lo_out = (e.out_lo != nullptr && row_ok && !(g.dbg & 64)) ? e.out_lo + lo_plane_index(row, 0, g.N) : nullptr;
+      if (lo_in != nullptr) {
+        // the low-plane blocks this thread will read, towards L2 now: the tile's MMAs are still running, and the loads in
+        // the epilogue body would otherwise each expose a DRAM round trip (no registers or shared memory to spare here)
+        const int jf = kShared ? 0 : group * kCPG;
+        for (int j = jf; j < jf + kCPG && n0 + j * 64 < g.N; ++j) {
+#pragma unroll
+          for (int q = (kShared ? group * 4 : 0); q < (kShared ? group * 4 + 4 : 8); ++q)
+            if (n0 + j * 64 + q * 8 < g.N)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(lo_in + (size_t)((n0 + j * 64 + q * 8) >> 3) * 256));
+        }
       }
+      // pivot of the row statistics: the mean the previous LayerNorm saw for this row (fetched one tile ahead)
+      const float pivot = pv_next;
+      pv_next = load_pivot(tile + cta_tile_step);
       const float* gate_row = e.row_gate != nullptr ? e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N : nullptr;
       if (kPair) mbar_wait_spin(&tfull_bar[as], aph);
       else mbar_wait(&tfull_bar[as], aph);
@@ -735,7 +744,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (!has_res) group_sync();   // (with a residual the wait on its arrival below orders the buffer reuse)
 
-      long long rs_sum = 0, rs_sq = 0;   // fixed point (stats.cuh)
+      // Row statistics: an fp32 partial per aligned 32-column piece (fixed column order), converted to fixed point and
+      // from then on added as integers.  The pieces are the same whatever tile width / epilogue grouping the launch
+      // picked, so the totals depend neither on the tile schedule nor on the batch size (stats.cuh).
+      long long rs_sum = 0, rs_sq = 0;
       // chunks of this group; the warp's last TMEM read of the tile hands the accumulator stage back to the MMA warp
       const int j_first = kShared ? 0 : group * kCPG;
       const int j_last = min(kShared ? 0 : group * kCPG + kCPG - 1, nvalid - 1);
@@ -772,17 +784,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           const int nb = n0 + j * 64 + hh * 32;
           const uint32_t c16 = (uint32_t)(hh * 4);
+          float ps = 0.0f, pq = 0.0f;
           switch (g.mode) {
-            case EPI_NONE: epi_row32<EPI_NONE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_RELU: epi_row32<EPI_RELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_GELU: epi_row32<EPI_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq); break;
-            case EPI_SE: epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq, gate_row); break;
-            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, rs_sum, rs_sq, nullptr, pivot, lo_in, lo_out); break;
+            case EPI_NONE: epi_row32<EPI_NONE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
+            case EPI_RELU: epi_row32<EPI_RELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
+            case EPI_GELU: epi_row32<EPI_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
+            case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
+            case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
+            case EPI_SE: epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq, gate_row); break;
+            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq, nullptr, pivot, lo_in, lo_out); break;
             default:
-              epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, rs_sum, rs_sq, pivot);
+              epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, ps, pq, pivot);
               break;
+          }
+          if (e.row_stats != nullptr) {
+            rs_sum += to_fx(ps);
+            rs_sq += to_fx(pq);
           }
         }
       }
@@ -864,7 +881,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 6] = clock64();
-      if (e.row_stats != nullptr && row < g.M && j_last >= j_first) {
+      if (e.row_stats != nullptr && row < g.M && j_last >= j_first && !(g.dbg & 32)) {
         long long* rec = e.row_stats + 3 * (size_t)row;
         fx_atomic_add_raw(rec, rs_sum);
         fx_atomic_add_raw(rec + 1, rs_sq);
@@ -1054,7 +1071,6 @@ int check_epilogue(const GemmEpilogue& epi, int N) {
               "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
   VIP_REQUIRE((epi.ln_stats == nullptr) == (epi.ln_colsum == nullptr), VIP_ERR_INVALID,
               "gemm: ln_stats and ln_colsum come together");
-  VIP_REQUIRE(epi.ln_stats == nullptr || epi.ln_cols > 0, VIP_ERR_INVALID, "gemm: ln_cols must be set with ln_stats");
   VIP_REQUIRE((epi.row_stats == nullptr && epi.gap == nullptr) || epi.out_bf16 != nullptr, VIP_ERR_UNSUPPORTED,
               "gemm: row_stats / gap need a bf16 output");
   VIP_REQUIRE(epi.gap == nullptr || epi.gap_rows > 0, VIP_ERR_INVALID, "gemm: gap_rows must be set with gap");
@@ -1295,12 +1311,11 @@ vip::GemmEpilogue to_epilogue(const vip_epilogue_t* p) {
   e.ldc = p->ldc;
   if (p->out_dtype == VIP_DTYPE_BF16) e.out_bf16 = reinterpret_cast<__nv_bfloat16*>(p->out);
   else e.out_f32 = reinterpret_cast<float*>(p->out);
-  e.ln_stats = reinterpret_cast<const long long*>(p->ln_stats);
+  e.ln_stats = p->ln_stats;
   e.ln_colsum = p->ln_colsum;
-  e.ln_cols = p->ln_cols;
-  e.ln_eps = p->ln_eps;
   e.row_stats = reinterpret_cast<long long*>(p->row_stats);
   e.gap = reinterpret_cast<long long*>(p->gap);
+  e.row_pivot = p->row_pivot;
   e.residual_lo = reinterpret_cast<const __nv_bfloat16*>(p->residual_lo);
   e.out_lo = reinterpret_cast<__nv_bfloat16*>(p->out_lo);
   e.gap_rows = p->gap_rows;

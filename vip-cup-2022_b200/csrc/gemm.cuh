@@ -18,7 +18,8 @@ enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 }
 //   v = rstd[m] * (v - mean[m] * ln_colsum[n])      if ln_stats   (LayerNorm of the A rows folded into the contraction:
 //                                                    B must hold gamma-scaled weights, bias must hold beta @ W + b)
 //   v += bias[n];  v = act(v);  v *= colscale[n];  v += residual[m, n];  store (bf16 or f32)
-//   row_stats[m] += (sum_n (out - p), sum_n (out - p)^2)   if row_stats (feeds the ln_stats of the next contraction;
+//   row_stats[m] += (sum_n (out - p), sum_n (out - p)^2)   if row_stats (vip_row_stats_finalize turns the records into the
+//                                                    ln_stats of the next contraction;
 //                                                    p = a per-row pivot, see stats.cuh; 64-bit fixed-point atomics:
 //                                                    the result does not depend on the order of the additions)
 //   gap[m / gap_rows, n] += out                      if gap        (GlobalAveragePooling partial sums, SE squeeze; fixed point)
@@ -34,17 +35,17 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16 = nullptr;        // [M, ldc] (exactly one of out_bf16 / out_f32)
   float* out_f32 = nullptr;
   int ldc = 0;
-  const long long* ln_stats = nullptr;      // [M, 3] row statistics records (stats.cuh) of the A rows over ln_cols columns
+  const float* ln_stats = nullptr;          // [M, 2] (mean, 1 / sigma) of the A rows (row_stats_finalize / layernorm / mlp_fused)
   const float* ln_colsum = nullptr;         // [N] column sums of the (gamma-scaled, bf16-rounded) weights
-  int ln_cols = 0;
-  float ln_eps = 1e-5f;
   long long* row_stats = nullptr;           // [M, 3] records accumulated with integer atomics; the caller zeroes it
   long long* gap = nullptr;                 // [ceil(M / gap_rows), N] fixed point, integer atomics; the caller zeroes it
   int gap_rows = 0;
   // SE bottleneck tail: v = relu((acc + bias[n]) * row_gate[m / gate_rows, n] + residual[m, n])
   const float* row_gate = nullptr;          // [ceil(M / gate_rows), N]
   int gate_rows = 0;
-  const __nv_bfloat16* residual_lo = nullptr;  // [M, ldr] low plane of the residual (null = zeros)
+  const float* row_pivot = nullptr;            // [M, 2]: .x = pivot of the row statistics (the previous LayerNorm's mean of
+                                               // the residual row: (mean, 1 / sigma) as in ln_stats); null = 0
+  const __nv_bfloat16* residual_lo = nullptr;  // low plane of the residual (blocked layout, stats.cuh; null = zeros)
   __nv_bfloat16* out_lo = nullptr;             // [M, ldc] low plane of the output (needs residual, no act / LN / gate)
 };
 

@@ -183,16 +183,16 @@ struct MlpCfg {
 };
 
 struct MlpArgs {
-  const long long* ln_stats; // [M, 3] row statistics records (stats.cuh) of the rows of x
+  const float* ln_stats;     // [M, 2] (mean, 1 / sigma) of the rows of x
   const bf16* x_lo;          // [M, C] low plane of x (two-plane residual stream) or null
   bf16* out_lo;              // [M, C] low plane of the output or null
   const float* colsum1;      // [HD]
   const float* bias1;        // [HD]
   const float* bias2;        // [C]
   bf16* out;                 // [M, C]
-  long long* row_stats;      // [M, 3] records of the output rows or null
+  float* ln_next;            // [M, 2] (mean, 1 / sigma) of the output rows for the next folded LayerNorm, or null
   long long M;
-  float ln_eps;
+  float next_eps;            // epsilon of that next LayerNorm
 };
 
 template <int C, int HD>
@@ -304,23 +304,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const float invC = 1.0f / (float)C;
     uint32_t job = 0;
     int n = g;
-    struct StatRec { long long s1, s2, pv; };
-    auto load_stats = [&](int tile_) -> StatRec {
+    auto load_stats = [&](int tile_) -> float2 {
       const long long m_ = (long long)tile_ * 128 + row;
-      if (tile_ >= total_tiles || m_ >= a.M) return StatRec{0, 0, 0};
-      const long long* rec = a.ln_stats + 3 * m_;
-      return StatRec{__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
+      if (tile_ >= total_tiles || m_ >= a.M) return make_float2(0.0f, 1.0f);
+      return __ldg(reinterpret_cast<const float2*>(a.ln_stats) + m_);
     };
-    StatRec st_next = load_stats(blockIdx.x + g * gridDim.x);
+    float2 st_next = load_stats(blockIdx.x + g * gridDim.x);
     for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, n += 2, ++job) {
       const int s = n % kStages;
       const long long m = (long long)tile * 128 + row;
       const bool row_ok = m < a.M;
-      const StatRec st = st_next;
+      const float2 st = st_next;
       st_next = load_stats(tile + 2 * gridDim.x);   // in flight during this tile
-      const RowMoments mo = row_moments(st.s1, st.s2, st.pv, invC, a.ln_eps);
-      const float rstd = mo.rstd;
-      const float nmr = -mo.mean * mo.rstd;
+      const float rstd = st.y;
+      const float nmr = -st.x * st.y;
 #ifdef VIP_MLP_TRACE
       const long long t0 = clock64();
 #endif
@@ -364,11 +361,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       float rs_sum = 0.0f, rs_sq = 0.0f;
       const uint8_t* xrow = sX + s * Cfg::kXBytes + row * 128;
       bf16* orow = a.out + m * C;
-      const bf16* lrow = (a.x_lo != nullptr && row_ok) ? a.x_lo + m * C : nullptr;
-      bf16* olrow = (a.out_lo != nullptr && row_ok) ? a.out_lo + m * C : nullptr;
-      // pivot of the output row statistics: the row's input value of column 0 (chunk 0 of k-block 0: swizzle row & 7)
-      float pivot = __bfloat162float(*reinterpret_cast<const bf16*>(xrow + ((row & 7) << 4)));
-      if (lrow != nullptr) pivot += __bfloat162float(lrow[0]);
+      // low planes: 32-row x 8-column blocks (stats.cuh), this row's slot of column block 0
+      const bf16* lrow = (a.x_lo != nullptr && row_ok) ? a.x_lo + lo_plane_index(m, 0, C) : nullptr;
+      bf16* olrow = (a.out_lo != nullptr && row_ok) ? a.out_lo + lo_plane_index(m, 0, C) : nullptr;
+      const float pivot = st.x;   // pivot of the output row's moments: the mean of the input row (stats.cuh)
       uint32_t ry[C / 32][32];
 #pragma unroll
       for (int c = 0; c < C / 32; ++c) tmem_ld32_nowait(tl + Cfg::Y_COL + c * 32, ry[c]);
@@ -386,7 +382,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const float bs[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t w[4], wl[4] = {0u, 0u, 0u, 0u};
           if (lrow != nullptr) {
-            const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lrow + col));
+            const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lrow + (size_t)(col >> 3) * 256));
             wl[0] = ul.x; wl[1] = ul.y; wl[2] = ul.z; wl[3] = ul.w;
           }
 #pragma unroll
@@ -402,15 +398,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             wl[t] = pack_bf16(v0 - __uint_as_float(w[t] << 16), v1 - __uint_as_float(w[t] & 0xffff0000u));
           }
           if (row_ok) *reinterpret_cast<uint4*>(orow + col) = make_uint4(w[0], w[1], w[2], w[3]);
-          if (olrow != nullptr) *reinterpret_cast<uint4*>(olrow + col) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+          if (olrow != nullptr) *reinterpret_cast<uint4*>(olrow + (size_t)(col >> 3) * 256) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
       }
       mbar_arrive(empty + s);   // the residual has been read: the stage may be refilled
-      if (a.row_stats != nullptr && row_ok) {
-        long long* rec = a.row_stats + 3 * m;
-        rec[0] = to_fx(rs_sum);
-        rec[1] = to_fx(rs_sq);
-        rec[2] = (long long)__float_as_int(pivot);
+      if (a.ln_next != nullptr && row_ok) {
+        // this thread owns the whole row: the moments of the next LayerNorm directly (pivoted one-pass form, stats.cuh)
+        const float d = rs_sum * invC;
+        const float var = fmaxf(rs_sq * invC - d * d, 0.0f);
+        *reinterpret_cast<float2*>(a.ln_next + 2 * m) = make_float2(pivot + d, 1.0f / sqrtf(var + a.next_eps));
       }
 #ifdef VIP_MLP_TRACE
       if (blockIdx.x == 0 && tid == 0) {
@@ -500,9 +496,9 @@ int launch_mlp(const bf16* x, long long M, const bf16* w1, int ldw1, const bf16*
 }  // namespace
 }  // namespace vip
 
-extern "C" int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int hidden, const int64_t* ln_stats,
-                                  float ln_eps, const void* w1, int ldw1, const float* colsum1, const float* bias1,
-                                  const void* w2, int ldw2, const float* bias2, void* out, void* out_lo, int64_t* row_stats,
+extern "C" int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int hidden, const float* ln_stats,
+                                  float next_eps, const void* w1, int ldw1, const float* colsum1, const float* bias1,
+                                  const void* w2, int ldw2, const float* bias2, void* out, void* out_lo, float* ln_next,
                                   void* stream) {
   using namespace vip;
   VIP_REQUIRE(x && ln_stats && w1 && colsum1 && bias1 && w2 && bias2 && out, VIP_ERR_INVALID, "vip_mlp_fused_bf16: null pointer");
@@ -510,16 +506,16 @@ extern "C" int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, 
   VIP_REQUIRE(ldw1 % 8 == 0 && ldw2 % 8 == 0 && ldw1 >= C && ldw2 >= hidden, VIP_ERR_INVALID,
               "vip_mlp_fused_bf16: weight leading dimensions (ldw1=%d ldw2=%d)", ldw1, ldw2);
   MlpArgs a;
-  a.ln_stats = reinterpret_cast<const long long*>(ln_stats);
+  a.ln_stats = ln_stats;
   a.x_lo = (const bf16*)x_lo;
   a.out_lo = (bf16*)out_lo;
   a.colsum1 = colsum1;
   a.bias1 = bias1;
   a.bias2 = bias2;
   a.out = (bf16*)out;
-  a.row_stats = reinterpret_cast<long long*>(row_stats);
+  a.ln_next = ln_next;
   a.M = M;
-  a.ln_eps = ln_eps;
+  a.next_eps = next_eps;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (C == 96 && hidden == 192) return launch_mlp<96, 192>((const bf16*)x, M, (const bf16*)w1, ldw1, (const bf16*)w2, ldw2, a, st);
   if (C == 64 && hidden == 192) return launch_mlp<64, 192>((const bf16*)x, M, (const bf16*)w1, ldw1, (const bf16*)w2, ldw2, a, st);

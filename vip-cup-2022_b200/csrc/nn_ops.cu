@@ -240,7 +240,7 @@ __global__ void scale_add_act_kernel(const bf16* __restrict__ y, const float* __
 template <int LPR, int J, int U>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        long long* __restrict__ row_stats, long long M, int C, float eps) {
+                                                        float* __restrict__ ln_next, float next_eps, long long M, int C, float eps) {
   pdl_trigger();
   pdl_wait();
   constexpr int RPW = 32 / LPR;  // rows per warp and group
@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       const float rstd = 1.0f / sqrtf(v * invC + eps);
-      // statistics record of the rounded output row (for a LayerNorm folded into the next GEMM), shifted by the row's
-      // first output element (stats.cuh)
+      // moments of the ROUNDED output row (for a LayerNorm folded into the next GEMM), sums shifted by the row's first
+      // output element (stats.cuh)
       float os = 0.0f, oq = 0.0f, pivot = 0.0f;
-      if (row_stats != nullptr) {
+      if (ln_next != nullptr) {
         const float g0 = __ldg(gamma), b0 = __ldg(beta);
         const float first = __bfloat162float(__float2bfloat16_rn(fmaf((f[u][0][0] - mean) * rstd, g0, b0)));  // valid in lane sub == 0
         pivot = __shfl_sync(0xffffffffu, first, rsel * LPR);
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
           for (int k = 0; k < 8; ++k) o8[k] = fmaf((f[u][j][k] - mean) * rstd, gg[k], bb[k]);
           const bf16x8 pk = pack8(o8);
           if (live) *reinterpret_cast<bf16x8*>(out + m * C + c8 * 8) = pk;
-          if (row_stats != nullptr) {
+          if (ln_next != nullptr) {
             float r8[8];
             unpack8(pk, r8);
 #pragma unroll
@@ -325,17 +325,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
           }
         }
       }
-      if (row_stats != nullptr) {
+      if (ln_next != nullptr) {
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) {
           os += __shfl_xor_sync(0xffffffffu, os, o);
           oq += __shfl_xor_sync(0xffffffffu, oq, o);
         }
         if (sub == 0 && live) {
-          long long* rec = row_stats + 3 * m;
-          rec[0] = to_fx(os);
-          rec[1] = to_fx(oq);
-          rec[2] = (long long)__float_as_int(pivot);
+          const float d = os * invC;
+          const float var2 = fmaxf(oq * invC - d * d, 0.0f);
+          *reinterpret_cast<float2*>(ln_next + 2 * m) = make_float2(pivot + d, 1.0f / sqrtf(var2 + next_eps));
         }
       }
     }
@@ -593,6 +592,39 @@ __global__ void scale_cast_fx_bf16_kernel(const long long* __restrict__ x, float
     out[i] = __float2bfloat16_rn(from_fx(x[i]) * scale);
 }
 
+// ---- row statistics records (stats.cuh; accumulated by the GEMM epilogues with integer atomics) -> (mean, 1 / sigma) per
+// row, the form the folded-LayerNorm consumers load (one coalesced 8-byte load per row and tile)
+__global__ void row_stats_finalize_kernel(const long long* __restrict__ rec, float2* __restrict__ out, long long M, float inv_cols,
+                                          float eps) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    const RowMoments mo = row_moments(__ldg(rec + 3 * m), __ldg(rec + 3 * m + 1), __ldg(rec + 3 * m + 2), inv_cols, eps);
+    out[m] = make_float2(mo.mean, mo.rstd);
+  }
+}
+
+// ---- FitWindow (models/gcvit/layers/feature.py:234-256) and the crop after the blocks (layers/level.py:61): a window of an
+// NHWC tensor copied into another geometry, zero outside the source.  out[n, y, x, :] = in[n, y - top, x - left, :].
+// Pixels are moved as 8-byte units, so the same kernel shifts activations (C % 4 == 0) and row statistics records.
+__global__ void pad_crop_kernel(const uint2* __restrict__ x, uint2* __restrict__ out, int N, int H, int W, int U, int Ho, int Wo,
+                                int top, int left) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)N * Ho * Wo * U;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(i % U);
+    long long t = i / U;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho), n = (int)(t / Ho);
+    const int sy = oy - top, sx = ox - left;
+    uint2 v = make_uint2(0u, 0u);
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = __ldg(x + (((long long)n * H + sy) * W + sx) * U + u);
+    out[i] = v;
+  }
+}
+
 // ---- out[g][n][k] = bf16(w[n][k] * gate[g][k]): the SE gate of an MBConv block (feature.py:49-66,144-150) scales the INPUT
 // channels of the 1x1 convolution that follows, y .* gate_g -> W; per image that is the same as contracting y with
 // W diag(gate_g), so the gate is folded into per-image copies of the (tiny) weight matrix instead of a pass over y.
@@ -661,9 +693,15 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   LAUNCH_CHECK();
 }
 
-extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, int64_t* row_stats_,
-                                  long long M, int C, float eps, void* stream) {
-  long long* row_stats = reinterpret_cast<long long*>(row_stats_);
+extern "C" int vip_row_stats_finalize(const int64_t* records, long long M, int cols, float eps, float* out, void* stream) {
+  VIP_REQUIRE(records && out && M > 0 && cols > 0, VIP_ERR_INVALID, "vip_row_stats_finalize: bad argument");
+  VIP_LAUNCH((row_stats_finalize_kernel), grid_for(M, 256), 256, 0, ST(stream), reinterpret_cast<const long long*>(records),
+             reinterpret_cast<float2*>(out), M, 1.0f / (float)cols, eps);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out, float* row_stats,
+                                  float next_eps, long long M, int C, float eps, void* stream) {
   VIP_REQUIRE(x && out && gamma && beta && C % 8 == 0 && C <= 1024, VIP_ERR_INVALID,
               "vip_layernorm_bf16: bad argument (C %% 8 == 0, C <= 1024)");
   const bf16* xp = (const bf16*)x;
@@ -672,12 +710,12 @@ extern "C" int vip_layernorm_bf16(const void* x, const float* gamma, const float
   cudaStream_t st = ST(stream);
   // narrow rows (C <= 128): 4 lanes per row (64 contiguous bytes per row and instruction), two row groups in flight.
   // Measured at [12.8 M, 96] on B200: 16 lanes per row 1.51 ms, one thread per row 1.42, 4 lanes 1.19, 4 lanes x 2 groups 1.12.
-  if (c8n <= 8) VIP_LAUNCH((layernorm_kernel<4, 2, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 12) VIP_LAUNCH((layernorm_kernel<4, 3, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 16) VIP_LAUNCH((layernorm_kernel<4, 4, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 32) VIP_LAUNCH((layernorm_kernel<32, 1, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else if (c8n <= 64) VIP_LAUNCH((layernorm_kernel<32, 2, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
-  else VIP_LAUNCH((layernorm_kernel<32, 4, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, M, C, eps);
+  if (c8n <= 8) VIP_LAUNCH((layernorm_kernel<4, 2, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
+  else if (c8n <= 12) VIP_LAUNCH((layernorm_kernel<4, 3, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
+  else if (c8n <= 16) VIP_LAUNCH((layernorm_kernel<4, 4, 2>), grid_for(M * 2, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
+  else if (c8n <= 32) VIP_LAUNCH((layernorm_kernel<32, 1, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
+  else if (c8n <= 64) VIP_LAUNCH((layernorm_kernel<32, 2, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
+  else VIP_LAUNCH((layernorm_kernel<32, 4, 1>), grid_for(M * 32, 256), 256, 0, st, xp, gamma, beta, op, row_stats, next_eps, M, C, eps);
   LAUNCH_CHECK();
 }
 
@@ -709,6 +747,17 @@ extern "C" int vip_head_f32(const float* feat, const float* w, const float* b, f
 extern "C" int vip_scale_cast_fx_bf16(const int64_t* x, float scale, void* out, long long n, void* stream) {
   VIP_REQUIRE(x && out, VIP_ERR_INVALID, "vip_scale_cast_fx_bf16: null pointer");
   VIP_LAUNCH((scale_cast_fx_bf16_kernel), grid_for(n, 256), 256, 0, ST(stream), reinterpret_cast<const long long*>(x), scale, (bf16*)out, n);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_pad_crop(const void* x, int N, int H, int W, int bytes_per_pixel, void* out, int Ho, int Wo, int top, int left,
+                            void* stream) {
+  VIP_REQUIRE(x && out && N > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && bytes_per_pixel > 0 && bytes_per_pixel % 8 == 0,
+              VIP_ERR_INVALID, "vip_pad_crop: bad argument (bytes_per_pixel must be a multiple of 8)");
+  VIP_REQUIRE((((uintptr_t)x | (uintptr_t)out) & 7) == 0, VIP_ERR_INVALID, "vip_pad_crop: unaligned pointer");
+  const int U = bytes_per_pixel / 8;
+  VIP_LAUNCH((pad_crop_kernel), grid_for((long long)N * Ho * Wo * U, 256), 256, 0, ST(stream), (const uint2*)x, (uint2*)out, N, H, W,
+             U, Ho, Wo, top, left);
   LAUNCH_CHECK();
 }
 

@@ -30,6 +30,14 @@ __device__ __forceinline__ void fx_atomic_add_raw(long long* p, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
 }
 
+// Low plane of the two-plane residual stream.  Only epilogues touch it, one thread per row, 8 columns (16 bytes) at a
+// time, so it is stored in the order the epilogue warps access it: blocks of 32 rows x 8 columns, 512 contiguous bytes
+// each (lane = row).  A warp's 16-byte access is then one fully coalesced 512-byte request instead of 32 requests a row
+// pitch apart.  Element (row, col) of an [rows (padded to 32), ncols] plane, in bf16 elements:
+__host__ __device__ __forceinline__ size_t lo_plane_index(long long row, int col, int ncols) {
+  return ((size_t)(row >> 5) * (size_t)(ncols >> 3) + (size_t)(col >> 3)) * 256 + (size_t)(row & 31) * 8 + (size_t)(col & 7);
+}
+
 struct RowMoments {
   float mean, rstd;
 };

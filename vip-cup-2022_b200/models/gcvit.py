@@ -230,34 +230,38 @@ class GCViT:
         y = nn.scale_add_act(y, gate, None, out=y)
         return nn.gemm(y.view(-1, c), d["pw"], residual=x.view(-1, c)).view(b, h, w, c)
 
-    def _reduce_apply(self, x, d, stride, out_stats=None):
+    def _reduce_apply(self, x, d, stride, ln_next=None):
         x = nn.layernorm(x, *d["n1"], eps=LN_EPS)
         x = self._mb_apply(x, d)
         x = nn.conv2d(x, d["red"], None, ksize=3, stride=stride, pad=1)
-        return nn.layernorm(x, *d["n2"], eps=LN_EPS, row_stats=out_stats)
+        return nn.layernorm(x, *d["n2"], eps=LN_EPS, ln_next=ln_next, next_eps=LN_EPS)
 
-    def _block(self, x, x_lo, stats, d, heads, ws, q_global, st_mid, st_out):
-        """GCViTBlock (block.py:60-81).  Both LayerNorms are folded into the contraction that consumes them: ``stats`` holds
-        the row statistics records of x, the proj / fc2 epilogues emit the records of their outputs.  The residual stream
+    def _block(self, x, x_lo, ln_in, d, heads, ws, q_global, ln_mid, ln_out, rec):
+        """GCViTBlock (block.py:60-81).  Both LayerNorms are folded into the contraction that consumes them: ``ln_in`` holds
+        (mean, 1 / sigma) of the rows of x; the proj / fc2 epilogues accumulate row statistics records of their outputs
+        (``rec`` [2, tokens, 3], integer atomics) that vip_row_stats_finalize turns into ``ln_mid`` / ``ln_out``; the fused
+        MLP kernel owns whole rows and writes ``ln_out`` itself.  The residual stream
         is carried in two bf16 planes (x = hi + lo, 16 mantissa bits): the hi plane is the operand of qkv / fc1, the lo
         plane only meets the proj / fc2 epilogues, so 2 x depth bf16 roundings of the running sum do not pile up
         (SURVEY.md 7 "fp32 residual stream if needed"; measured: 1.5e-2 -> 4e-3 logit error on GCViT-small)."""
         b, h, w, c = x.shape
         x2 = x.view(-1, c)
         wq, bq, cq = d["qkv"]
-        qkv = nn.gemm(x2, wq, bias=bq, ln_stats=stats, ln_colsum=cq, ln_cols=c, ln_eps=LN_EPS)
+        qkv = nn.gemm(x2, wq, bias=bq, ln_stats=ln_in, ln_colsum=cq)
         a = nn.window_attention(qkv, q_global, d["rel"], b, h, w, c, ws, heads)
-        lo1 = torch.empty_like(x2) if TWO_PLANE else None
-        x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=st_mid, residual_lo=x_lo, out_lo=lo1)
+        lo1 = nn.lo_plane(x2.shape[0], c, x2.device) if TWO_PLANE else None
+        x2 = nn.gemm(a, *d["proj"], residual=x2, row_stats=rec[0], residual_lo=x_lo, out_lo=lo1, row_pivot=ln_in)
+        nn.finalize_stats(rec[0], c, LN_EPS, out=ln_mid)
         w1, b1, c1 = d["fc1"]
         if FUSED_MLP and (c, w1.shape[0]) in nn.MLP_FUSED_SHAPES:
             # narrow levels: both contractions in one kernel, the [tokens, hidden] tensor never reaches HBM
-            res = nn.mlp_fused(x2, st_mid, w1, c1, b1, *d["fc2"], ln_eps=LN_EPS, row_stats=st_out, x_lo=lo1, want_lo=TWO_PLANE)
+            res = nn.mlp_fused(x2, ln_mid, w1, c1, b1, *d["fc2"], next_eps=LN_EPS, ln_next=ln_out, x_lo=lo1, want_lo=TWO_PLANE)
             x2, lo2 = res if TWO_PLANE else (res, None)
         else:
-            hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=st_mid, ln_colsum=c1, ln_cols=c, ln_eps=LN_EPS)
-            lo2 = torch.empty_like(x2) if TWO_PLANE else None
-            x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=st_out, residual_lo=lo1, out_lo=lo2)
+            hdn = nn.gemm(x2, w1, bias=b1, act="gelu", ln_stats=ln_mid, ln_colsum=c1)
+            lo2 = nn.lo_plane(x2.shape[0], c, x2.device) if TWO_PLANE else None
+            x2 = nn.gemm(hdn, *d["fc2"], residual=x2, row_stats=rec[1], residual_lo=lo1, out_lo=lo2, row_pivot=ln_mid)
+            nn.finalize_stats(rec[1], c, LN_EPS, out=ln_out)
         return x2.view(b, h, w, c), lo2
 
     def features(self, x, taps=None):
@@ -270,34 +274,62 @@ class GCViT:
             x = nn.conv2d(x, *p["proj"], ksize=3, stride=2, pad=1)
         nimg = x.shape[0]
 
-        def level_stats(i, tokens):  # one zeroed arena of row statistics records per level: [1 + 2*depth, tokens, 3]
-            return nn.row_stats_buffer(1 + 2 * cfg["depths"][i], tokens, device=x.device)
+        def level_stats(i, tokens):
+            """Per level: (mean, 1 / sigma) slots [1 + 2 depth, tokens, 2] and one zeroed arena of row statistics records
+            [2 depth, tokens, 3] for the epilogues that accumulate them."""
+            depth = cfg["depths"][i]
+            return (torch.empty((1 + 2 * depth, tokens, 2), dtype=torch.float32, device=x.device),
+                    nn.row_stats_buffer(2 * depth, tokens, device=x.device))
 
-        h0 = (x.shape[1] + 2 - 3) // self.first_strides + 1
-        st = level_stats(0, nimg * h0 * h0)
-        x = self._reduce_apply(x, p["conv_down"], self.first_strides, out_stats=st[0])
+        def fit(v, ws):   # FitWindow (feature.py:240-249): the size a map is padded to, and the top / left share of the pad
+            vp = (v + ws - 1) // ws * ws
+            return vp, (vp - v) // 2
+
+        def reduce_into_level(x_in, d, stride, i):
+            """ReduceSize whose output feeds level i: returns (x, level statistics arena); ln[0] = (mean, 1 / sigma) of x's
+            rows, laid out for the FitWindow-padded map when the level pads (padded rows are all zero: the folded
+            LayerNorm then yields beta W + b for them, exactly what LayerNorm of a zero row gives)."""
+            ho, wo = (x_in.shape[1] + 2 - 3) // stride + 1, (x_in.shape[2] + 2 - 3) // stride + 1
+            ws = cfg["window_size"][i]
+            (hp, _), (wp, _) = fit(ho, ws), fit(wo, ws)
+            arena = level_stats(i, nimg * hp * wp)
+            if (hp, wp) == (ho, wo):
+                return self._reduce_apply(x_in, d, stride, ln_next=arena[0][0]), arena
+            ln_in = torch.empty((nimg * ho * wo, 2), dtype=torch.float32, device=x_in.device)
+            x_out = self._reduce_apply(x_in, d, stride, ln_next=ln_in)
+            nn.pad_crop(ln_in.view(nimg, ho, wo, 2), hp, wp, fit(ho, ws)[1], fit(wo, ws)[1], out=arena[0][0].view(nimg, hp, wp, 2))
+            return x_out, arena
+
+        x, st = reduce_into_level(x, p["conv_down"], self.first_strides, 0)
         if taps is not None:
             taps["stem"] = x
         for i, depth in enumerate(cfg["depths"]):
             ws, heads = cfg["window_size"][i], cfg["num_heads"][i]
             b, h, w, c = x.shape
-            if h % ws or w % ws:
-                raise nn.VipError(f"GCViT level {i}: feature map {h}x{w} is not a multiple of window {ws} "
-                                  "(FitWindow padding for non-224 inputs is not built)")
+            (hp, top), (wp, left) = fit(h, ws), fit(w, ws)
+            padded = (hp, wp) != (h, w)
+            if padded:
+                # FitWindow: zero padding on both sides; the padded tokens take part in attention like any other token, and the
+                # level's output is the TOP-LEFT h x w corner of the padded map (level.py:49,61 -- mirrored as it is)
+                x = nn.pad_crop(x, hp, wp, top, left)
             q = x
             for k, keep in enumerate(KEEP_DIMS[i]):
                 q = self._mb_apply(q, p[f"q{i}_{k}"])
                 if not keep:
                     q = nn.maxpool3s2(q)
+            if q.shape[1] != ws or q.shape[2] != ws:
+                raise nn.VipError(f"GCViT level {i}: global query map {q.shape[1]}x{q.shape[2]} does not match window {ws} "
+                                  f"(input {self.input_shape}; attention.py:65 has the same requirement)")
             q = q.view(b, ws * ws, c)
             x_lo = None   # the level starts from a LayerNorm output: low plane = 0
+            ln, rec = st
             for j in range(depth):
-                x, x_lo = self._block(x, x_lo, st[2 * j], p[f"b{i}_{j}"], heads, ws, q if j % 2 else None, st[2 * j + 1],
-                                      st[2 * j + 2])
+                x, x_lo = self._block(x, x_lo, ln[2 * j], p[f"b{i}_{j}"], heads, ws, q if j % 2 else None, ln[2 * j + 1],
+                                      ln[2 * j + 2], rec[2 * j: 2 * j + 2])
+            if padded:
+                x = nn.pad_crop(x, h, w, 0, 0)
             if i < 3:
-                ho = (h + 2 - 3) // 2 + 1
-                st = level_stats(i + 1, b * ho * ho)
-                x = self._reduce_apply(x, p[f"down{i}"], 2, out_stats=st[0])
+                x, st = reduce_into_level(x, p[f"down{i}"], 2, i + 1)
             if taps is not None:
                 taps[f"level{i}"] = x
         return x

@@ -34,25 +34,59 @@ def row_stats_buffer(*lead, device):
     return zero_(torch.empty((*lead, 3), dtype=STATS, device=device))
 
 
-def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=None, ln_colsum=None, ln_cols=0,
-              ln_eps=1e-5, row_stats=None, gap=None, gap_rows=0, row_gate=None, gate_rows=0, residual_lo=None, out_lo=None):
+def lo_plane(m, n, device):
+    """Uninitialised low plane for an [m, n] two-plane tensor (opaque blocked layout, see include/vipcup.h)."""
+    return torch.empty(((m + 31) // 32 * 32, n), dtype=BF16, device=device)
+
+
+def lo_plane_to_rows(lo, m):
+    """Blocked low plane -> ordinary [m, n] row-major tensor (tests / debugging)."""
+    mp, n = lo.shape
+    return lo.view(mp // 32, n // 8, 32, 8).permute(0, 2, 1, 3).reshape(mp, n)[:m]
+
+
+def lo_plane_from_rows(x):
+    """[m, n] row-major bf16 -> blocked low plane."""
+    m, n = x.shape
+    mp = (m + 31) // 32 * 32
+    xp = torch.zeros((mp, n), dtype=x.dtype, device=x.device)
+    xp[:m] = x
+    return xp.view(mp // 32, 32, n // 8, 8).permute(0, 2, 1, 3).contiguous().view(mp, n)
+
+
+def finalize_stats(records, cols, eps=1e-5, out=None):
+    """int64 [M, 3] row statistics records -> f32 [M, 2] (mean, 1 / sigma): the ``ln_stats`` operand of a folded LayerNorm."""
+    _chk(records, "records", STATS)
+    m = records.numel() // 3
+    if out is None:
+        out = torch.empty((m, 2), dtype=torch.float32, device=records.device)
+    _chk(out, "out", torch.float32)
+    _lib.check(_lib.lib().vip_row_stats_finalize(_p(records), m, int(cols), float(eps), _p(out), _st()), "vip_row_stats_finalize")
+    return out
+
+
+def _epilogue(out, bias=None, act=None, colscale=None, residual=None, ln_stats=None, ln_colsum=None,
+              row_stats=None, gap=None, gap_rows=0, row_gate=None, gate_rows=0, residual_lo=None, out_lo=None,
+              row_pivot=None):
     _chk(residual, "residual"), _chk(residual_lo, "residual_lo"), _chk(out_lo, "out_lo")
-    for name, t in (("bias", bias), ("colscale", colscale), ("ln_colsum", ln_colsum), ("row_gate", row_gate)):
+    for name, t in (("bias", bias), ("colscale", colscale), ("ln_colsum", ln_colsum), ("row_gate", row_gate),
+                    ("ln_stats", ln_stats), ("row_pivot", row_pivot)):
         _chk(t, name, torch.float32)
-    for name, t in (("ln_stats", ln_stats), ("row_stats", row_stats), ("gap", gap)):
+    for name, t in (("row_stats", row_stats), ("gap", gap)):
         _chk(t, name, STATS)
-    for name, t in (("ln_stats", ln_stats), ("row_stats", row_stats)):
-        if t is not None and (t.shape[-1] != 3 or t.numel() != 3 * out.shape[0]):
-            raise VipError(f"{name} must be int64 [M, 3] row statistics records")
+    if ln_stats is not None and ln_stats.numel() != 2 * out.shape[0]:
+        raise VipError("ln_stats must be f32 [M, 2] (mean, 1 / sigma)")
+    if row_stats is not None and row_stats.numel() != 3 * out.shape[0]:
+        raise VipError("row_stats must be int64 [M, 3] row statistics records")
     e = _lib.Epilogue()
     e.bias, e.act, e.colscale = _p(bias), ACT[act], _p(colscale)
     e.residual, e.ldr = _p(residual), (0 if residual is None else residual.stride(0))
     e.out, e.ldc = _p(out), out.stride(0)
     e.out_dtype = _lib.VIP_DTYPE_BF16 if out.dtype == BF16 else _lib.VIP_DTYPE_F32
-    e.ln_stats, e.ln_colsum, e.ln_cols, e.ln_eps = _p(ln_stats), _p(ln_colsum), int(ln_cols), float(ln_eps)
+    e.ln_stats, e.ln_colsum = _p(ln_stats), _p(ln_colsum)
     e.row_stats, e.gap, e.gap_rows = _p(row_stats), _p(gap), int(gap_rows)
     e.row_gate, e.gate_rows = _p(row_gate), int(gate_rows)
-    e.residual_lo, e.out_lo = _p(residual_lo), _p(out_lo)
+    e.residual_lo, e.out_lo, e.row_pivot = _p(residual_lo), _p(out_lo), _p(row_pivot)
     return e
 
 
@@ -190,13 +224,15 @@ def scale_add_act(y, gate=None, shortcut=None, act=None, out=None):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, row_stats=None):
+def layernorm(x, gamma, beta, eps=1e-5, ln_next=None, next_eps=1e-5):
+    """``ln_next`` (f32 [M, 2]) receives (mean, 1 / sqrt(var + next_eps)) of the output rows: the ``ln_stats`` of a
+    LayerNorm folded into the contraction that consumes the output."""
     _chk(x, "x"), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32)
-    _chk(row_stats, "row_stats", STATS)
+    _chk(ln_next, "ln_next", torch.float32)
     c = x.shape[-1]
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), _p(row_stats), x.numel() // c, c, eps,
-                                             _st()), "vip_layernorm_bf16")
+    _lib.check(_lib.lib().vip_layernorm_bf16(_p(x), _p(gamma), _p(beta), _p(out), _p(ln_next), float(next_eps),
+                                             x.numel() // c, c, eps, _st()), "vip_layernorm_bf16")
     return out
 
 
@@ -216,6 +252,19 @@ def maxpool3s2(x):
     n, h, w, c = x.shape
     out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=BF16, device=x.device)
     _lib.check(_lib.lib().vip_maxpool3s2_bf16(_p(x), _p(out), n, h, w, c, _st()), "vip_maxpool3s2_bf16")
+    return out
+
+
+def pad_crop(x, ho, wo, top=0, left=0, out=None):
+    """out[n, y, x] = x[n, y - top, x - left] (zero outside): FitWindow padding / crop of an NHWC tensor [N,H,W,C] (bf16
+    activations or int64 [N,H,W,3] row statistics records)."""
+    if not x.is_cuda or not x.is_contiguous() or x.dim() != 4:
+        raise VipError("pad_crop: x must be a contiguous CUDA [N,H,W,C] tensor")
+    n, h, w, c = x.shape
+    bpp = c * x.element_size()
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().vip_pad_crop(_p(x), n, h, w, bpp, _p(out), ho, wo, top, left, _st()), "vip_pad_crop")
     return out
 
 
@@ -249,20 +298,20 @@ def cast_bf16(x_f32):
 MLP_FUSED_SHAPES = {(96, 192), (64, 192)}
 
 
-def mlp_fused(x, ln_stats, w1, colsum1, bias1, w2, bias2, ln_eps=1e-5, row_stats=None, x_lo=None, want_lo=False):
+def mlp_fused(x, ln_stats, w1, colsum1, bias1, w2, bias2, next_eps=1e-5, ln_next=None, x_lo=None, want_lo=False):
     """x + fc2(gelu(fc1(LayerNorm(x)))) in one kernel (hidden activations stay on the SM); arguments as for the two
     ``gemm`` calls it replaces: w1 [hidden, C] gamma-scaled + colsum1 + bias1 (LayerNorm folded), w2 [C, hidden] + bias2.
     Only for (C, hidden) in MLP_FUSED_SHAPES.  ``x_lo`` / ``want_lo``: low planes of the two-plane residual stream;
     with want_lo returns (out, out_lo)."""
-    _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2"), _chk(ln_stats, "ln_stats", STATS), _chk(x_lo, "x_lo")
-    _chk(row_stats, "row_stats", STATS)
+    _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2"), _chk(ln_stats, "ln_stats", torch.float32), _chk(x_lo, "x_lo")
+    _chk(ln_next, "ln_next", torch.float32)
     m, c = x.shape
     hidden = w1.shape[0]
     out = torch.empty_like(x)
-    out_lo = torch.empty_like(x) if want_lo else None
-    rc = _lib.lib().vip_mlp_fused_bf16(_p(x), _p(x_lo), m, c, hidden, _p(ln_stats), float(ln_eps), _p(w1), w1.stride(0),
+    out_lo = lo_plane(m, c, x.device) if want_lo else None
+    rc = _lib.lib().vip_mlp_fused_bf16(_p(x), _p(x_lo), m, c, hidden, _p(ln_stats), float(next_eps), _p(w1), w1.stride(0),
                                        _p(colsum1), _p(bias1), _p(w2), w2.stride(0), _p(bias2), _p(out), _p(out_lo),
-                                       _p(row_stats), _st())
+                                       _p(ln_next), _st())
     _lib.check(rc, "vip_mlp_fused_bf16")
     return (out, out_lo) if want_lo else out
 
