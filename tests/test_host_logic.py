@@ -71,12 +71,34 @@ def test_scan_checkpoints_errors(tmp_path):
     assert out[0][1] == [200, 200] and out[0][0][0].endswith("fold0.npz")
 
 
-def test_augment_flag_statistics():
+def test_philox_known_answers():
+    """Philox-4x32-10 against the known-answer vectors of the Random123 distribution (kat_vectors): the generator family
+    of tf.random.uniform (dataset/augment.py:11-19), used here as a pure function of (image index, TTA pass)."""
+    from vipcup_b200.dataset import philox4x32_10, uniform_from_bits
+
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(v) for v in philox4x32_10([ctr], key)[0]) == out
+    u = uniform_from_bits(np.array([0, 0xFFFFFFFF, 0x80000000], np.uint32))
+    assert u[0] == 0.0 and u[1] == np.float32(1.0) - np.float32(2.0 ** -23) and u[2] == 0.5
+
+
+def test_augment_flags_statistics_and_order_independence():
     from vipcup_b200.dataset import draw_augment_flags
 
-    f = draw_augment_flags(200000, np.random.default_rng(42))
+    f = draw_augment_flags(np.arange(200000), 0, 42)
     assert abs((f & 1).mean() - 0.8 * 0.5) < 0.01 and abs(((f >> 1) & 1).mean() - 0.4) < 0.01
-    assert abs(((f >> 2) & 1).mean() - 0.8 * 0.3) < 0.01
+    assert abs(((f >> 2) & 1).mean() - 0.8 * 0.3) < 0.01 and abs((f == 0).mean() - (0.2 + 0.8 * 0.25 * 0.7)) < 0.01
+    # counter-based: the decision of image i in pass p does not depend on which images are asked for together with it
+    idx = np.array([7, 123456, 3, 99999])
+    assert np.array_equal(draw_augment_flags(idx, 0, 42), f[idx])
+    assert np.array_equal(draw_augment_flags(np.arange(1000, 2000), 0, 42), f[1000:2000])
+    g = draw_augment_flags(np.arange(200000), 1, 42)
+    assert 0.1 < (f == g).mean() < 0.3                      # another pass: independent decisions (sum p_k^2 = 0.19)
+    assert not np.array_equal(draw_augment_flags(np.arange(1000), 0, 43), f[:1000])
 
 
 def _worker(rank, world, port, tmp, n, q):

@@ -104,11 +104,8 @@ def test_main_py_tta_multibatch_mixed_sizes(workdir, tmp_path):
 
     test_csv = pd.read_csv(os.path.join(data, "input.csv"))
     imgs = [np.asarray(Image.open(os.path.join(data, f)).convert("RGB")) for f in test_csv.filename]
-    rng = np.random.default_rng(42)                    # CFG.seed (main.py:224); decisions are drawn per decoded batch
-    flags = []
-    for _ in range(2):
-        fl = [draw_augment_flags(len(range(i0, min(n, i0 + 128))), rng) for i0 in range(0, n, 128)]
-        flags.append(np.concatenate(fl))
+    # CFG.seed = 42 (main.py:224); decisions are a pure function of (image position, pass, seed)
+    flags = [draw_augment_flags(np.arange(n), p, 42) for p in range(2)]
     p = make_decided_dataset.oracle_model_probs(models, name, imgs, tta_flags=flags)
     ref = 1 - p.reshape(2, n, -1).mean(0)[:, 0]
     err = np.abs(per_model[name].logit.values - ref)

@@ -4,9 +4,10 @@ build_augmenter 50-59, build_dataset 64-102).
 What changed underneath: tf.io.read_file / tf.image.decode_jpeg run on host threads through Pillow (the same
 libjpeg-turbo defaults TF uses: ISLOW IDCT, fancy upsampling) into pinned uint8 staging buffers; everything after the
 decode -- cast, bicubic resize, /255, the augmentations -- is ONE fused CUDA kernel (vip_preprocess) that writes the
-[B,H,W,3] batch in device memory, where the backbones consume it.  tf.data's RNG cannot be reproduced, so the TTA
-decisions of apply_augment (dataset/augment.py:153-182: p=0.8 gate, hflip 0.5, vflip 0.5, gray 0.3) are drawn from a
-numpy Generator seeded with CFG.seed and passed to the kernel as explicit per-image flags."""
+[B,H,W,3] batch in device memory, where the backbones consume it.  tf.data's RNG stream cannot be reproduced, so
+the TTA decisions of apply_augment (dataset/augment.py:153-182: p=0.8 gate, hflip 0.5, vflip 0.5, gray 0.3) are drawn from
+a counter-based Philox-4x32-10 keyed by CFG.seed and indexed by (image position, TTA pass) -- independent of batching and
+sharding -- and passed to the kernel as explicit per-image flags."""
 from __future__ import annotations
 
 import os
@@ -46,20 +47,50 @@ def build_decoder(with_labels, img_size, CFG, ext="jpg"):
     return decode_with_labels if with_labels else decode
 
 
-def draw_augment_flags(n, rng):
-    """apply_augment (dataset/augment.py:153-182) as explicit decisions: returns uint8 flags [n]."""
-    gate = rng.random(n) <= 0.80                      # `if random_float() > augment_prob: return image`
-    h = (rng.random(n) < 0.5) & gate                  # RandomFlip prob_hflip=0.5
-    v = (rng.random(n) < 0.5) & gate                  # prob_vflip=0.5
-    g = (rng.random(n) < 0.3) & gate                  # RandomGray prob=0.3
+def philox4x32_10(counter, key):
+    """Philox-4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"; the generator behind
+    tf.random.uniform, dataset/augment.py:11-19) on an array of counters: counter uint32 [n, 4], key (k0, k1) -> uint32
+    [n, 4].  Counter-based: every output depends only on (counter, key), not on how many numbers were drawn before."""
+    c = np.array(counter, dtype=np.uint64, copy=True).reshape(-1, 4)
+    k0, k1 = np.uint64(int(key[0]) & 0xFFFFFFFF), np.uint64(int(key[1]) & 0xFFFFFFFF)
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    w0, w1 = np.uint64(0x9E3779B9), np.uint64(0xBB67AE85)
+    for _ in range(10):
+        p0, p1 = m0 * c[:, 0], m1 * c[:, 2]                       # 32 x 32 -> 64-bit products
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0, k1 = (k0 + w0) & mask, (k1 + w1) & mask
+    return c.astype(np.uint32)
+
+
+def uniform_from_bits(u32):
+    """uint32 -> float32 in [0, 1) the way TF's random ops do it: 23 random mantissa bits of a float in [1, 2), minus 1."""
+    return ((np.asarray(u32, np.uint32) >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+
+
+def draw_augment_flags(indices, pass_idx, seed):
+    """apply_augment (dataset/augment.py:153-182) as explicit per-image decisions, uint8 flags [n].
+
+    TF's stateful RNG inside a parallel tf.data map cannot be reproduced; the decisions here come from the same generator
+    family used as a pure function: Philox(counter = (image index in the CSV, TTA pass, 0, 0), key = (seed, 0)) gives the
+    four uniforms of one image -- gate (`random_float() > 0.8` returns the image unchanged), hflip < 0.5, vflip < 0.5
+    (RandomFlip, augment.py:115-120), gray < 0.3 (RandomGray, 142-146).  They do not depend on the batch size, the order of
+    evaluation or the number of GPUs the list is sharded over."""
+    idx = np.asarray(indices, dtype=np.uint64).reshape(-1)
+    ctr = np.stack([idx & np.uint64(0xFFFFFFFF), np.full_like(idx, int(pass_idx)), idx >> np.uint64(32), np.zeros_like(idx)], 1)
+    u = uniform_from_bits(philox4x32_10(ctr, (int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)))
+    gate = ~(u[:, 0] > np.float32(0.80))
+    h = (u[:, 1] < np.float32(0.5)) & gate
+    v = (u[:, 2] < np.float32(0.5)) & gate
+    g = (u[:, 3] < np.float32(0.3)) & gate
     return (h * ops.FLAG_HFLIP + v * ops.FLAG_VFLIP + g * ops.FLAG_GRAY).astype(np.uint8)
 
 
 def build_augmenter(with_labels=True, img_size=(200, 200), CFG=None):
-    """Returns ``augment(n) -> flags`` drawing the per-image decisions for one pass over ``n`` images."""
-    def augment(n):
-        rng = getattr(CFG, "_rng", None) or np.random.default_rng(getattr(CFG, "seed", 42))
-        return draw_augment_flags(n, rng)
+    """Returns ``augment(indices, pass_idx) -> flags``: the decisions of one TTA pass for the images with those positions
+    in the input CSV."""
+    def augment(indices, pass_idx=0):
+        return draw_augment_flags(indices, pass_idx, getattr(CFG, "seed", 42))
 
     return augment
 
@@ -68,8 +99,10 @@ class DeviceDataset:
     """Iterable of device batches [B,H,W,3] (bf16 by default).  ``repeat`` / ``steps`` semantics of tf.data are
     replaced by explicit passes: iterating yields ceil(N/B) batches of one pass; call again for the next TTA pass."""
 
-    def __init__(self, paths, batch_size, img_size, decode_fn, augment_fn, augment, out_dtype, device, workers):
+    def __init__(self, paths, batch_size, img_size, decode_fn, augment_fn, augment, out_dtype, device, workers,
+                 index_offset=0):
         self.paths, self.batch_size, self.img_size = list(paths), int(batch_size), tuple(int(v) for v in img_size)
+        self.index_offset, self.passes_done = int(index_offset), 0   # position of paths[0] in the whole list; TTA pass counter
         self.decode_fn, self.augment_fn, self.augment = decode_fn, augment_fn, augment
         self.out_dtype, self.device = out_dtype, device
         self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
@@ -97,9 +130,14 @@ class DeviceDataset:
                 pending.append(self.prefetcher.submit(self._decode_batch, self.paths[j0: j0 + self.batch_size]))
             yield i0, imgs
 
+    def flags_for(self, i0, n, pass_idx):
+        """Augmentation decisions of images [i0, i0 + n) of this dataset in TTA pass ``pass_idx``."""
+        return self.augment_fn(self.index_offset + i0 + np.arange(n), pass_idx)
+
     def __iter__(self):
-        for _, imgs in self.host_batches(depth=1):
-            flags = self.augment_fn(len(imgs)) if self.augment else None
+        pass_idx, self.passes_done = self.passes_done, self.passes_done + 1
+        for i0, imgs in self.host_batches(depth=1):
+            flags = self.flags_for(i0, len(imgs), pass_idx) if self.augment else None
             yield self._to_device(imgs, flags)
 
     def stage(self, imgs):
@@ -138,7 +176,7 @@ class DeviceDataset:
 
 def build_dataset(paths, labels=None, batch_size=32, cache=True, decode_fn=None, augment_fn=None, dim=(200, 200),
                   augment=True, repeat=True, shuffle=1024, cache_dir="", drop_remainder=False, CFG=None,
-                  out_dtype=torch.bfloat16, device=None, workers=None):
+                  out_dtype=torch.bfloat16, device=None, workers=None, index_offset=0):
     """Same arguments as dataset/dataset.py:64-102 (labels / cache / shuffle / repeat only matter for training and are
     accepted and ignored on this inference path)."""
     if labels is not None:
@@ -149,4 +187,4 @@ def build_dataset(paths, labels=None, batch_size=32, cache=True, decode_fn=None,
         augment_fn = build_augmenter(False, img_size=CFG.img_size, CFG=CFG)
     device = device or torch.device("cuda", torch.cuda.current_device())
     return DeviceDataset(paths, batch_size, CFG.img_size, decode_fn, augment_fn, augment, out_dtype, device,
-                         workers or min(32, os.cpu_count() or 4))
+                         workers or min(32, os.cpu_count() or 4), index_offset=index_offset)

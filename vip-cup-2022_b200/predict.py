@@ -119,7 +119,7 @@ def _load_model(model_name, model_path, dim, device):
     return model.load_weights(W)
 
 
-def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None):
+def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, index_offset=0):
     """Device half of ``predict_soln`` for this rank's shard: every fold of every registry entry over ``local_paths``.
     Returns (list over (model, fold) of float32 [tta * n_local, k] arrays, pass-major like ``model.predict`` on the
     repeated dataset (main.py:109-111), fold counts per model).
@@ -149,12 +149,12 @@ def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None):
     chunk = max(e["bs"] for e in entries)
     CFG.batch_size, CFG.img_size = chunk, entries[0]["dim"]
     ds = build_dataset(local_paths, labels=None, augment=tta > 1, repeat=True, cache=False, shuffle=False,
-                       batch_size=chunk, drop_remainder=False, CFG=CFG, device=dev)
+                       batch_size=chunk, drop_remainder=False, CFG=CFG, device=dev, index_offset=index_offset)
     shared, outs = {}, []
     use_graph = os.environ.get("VIP_GRAPH", "1") != "0"
-    for _ in range(tta):
+    for pass_idx in range(tta):
         for i0, imgs in ds.host_batches():
-            flags_h = ds.augment_fn(len(imgs)) if tta > 1 else None
+            flags_h = ds.flags_for(i0, len(imgs), pass_idx) if tta > 1 else None
             src = ds.stage(imgs)
             flags = None if flags_h is None else torch.from_numpy(np.ascontiguousarray(flags_h)).to(dev, non_blocking=True)
             for e in entries:
@@ -226,7 +226,7 @@ def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None, runner_cac
                 raw.append(predict_fn(model_name, model_path, dim, local_paths))
             fold_counts.append(len(model_paths))
     else:
-        raw, fold_counts = predict_device(CFG, local_paths, tta, verbose, runner_cache)
+        raw, fold_counts = predict_device(CFG, local_paths, tta, verbose, runner_cache, index_offset=lo)
     local_rows = [aggregate_model(np.asarray(pred, np.float32), tta, n_local, CFG.agg)[:, 0] for pred in raw]
 
     # one exchange step: [sum(folds), n_local] float32 per rank -> [sum(folds), N] everywhere
