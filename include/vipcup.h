@@ -175,6 +175,16 @@ int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, voi
  * SE squeeze (GlobalAveragePooling, feature.py:55) without a second pass over the map. */
 int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap, int N, int H, int W, int C, int gelu,
                        void* cuda_stream);
+/* Depthwise K x K convolution, NHWC bf16, explicit zero padding (pad_top / pad_left; the bottom / right padding follows from
+ * Ho / Wo), w f32 [K, K, C], bias f32 [C] or NULL, act 0 none / 1 swish / 2 gelu (erf) / 3 relu, gap as for
+ * vip_dwconv3x3_bf16.  Built: K 3 | 5 with stride 1 | 2, K 7 with stride 1.
+ * ConvNeXt: models/tfimm/architectures/convnext.py:192-198 (ZeroPadding2D(3) + DepthwiseConv2D(7) + bias);
+ * EfficientNet MBConv: keras_cv_attention_models/efficientnet/efficientnet_v2.py:80-96 (BN folded by the caller). */
+int vip_dwconv_bf16(const void* x, const float* w, const float* bias, void* out, int64_t* gap, int N, int H, int W, int C,
+                    int ksize, int stride, int pad_top, int pad_left, int Ho, int Wo, int act, void* cuda_stream);
+/* LayerNormalization of pooled f32 vectors [M, C] -> f32 (ConvNeXt head, convnext.py:432-436). */
+int vip_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, int M, int C, float eps,
+                      void* cuda_stream);
 /* ZeroPadding2D(1) + MaxPool2D(3,2,'valid') (padded zeros take part in the max): gcvit feature.py:139,151-152 */
 int vip_maxpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
 /* Window attention, head_dim 32, window partition/reverse folded into addressing: gcvit attention.py:52-83, window.py:3-14.

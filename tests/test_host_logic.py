@@ -51,9 +51,9 @@ def test_config_and_registry():
     assert dict2cfg({"class_labels": [0, 1], "class_names": ["real", "syn"]}).label2name == {0: "real", 1: "syn"}
     assert registry.arch_of("ResNetRS50-200x200") == "ResNetRS50"
     assert 8 * registry.NAME2BS.get("ResNetRS50-200x200", 16) == 128      # main.py:85
-    assert {"ResNetRS50", "ResNetRS101", "GCViTTiny", "GCViTSmall"} <= set(registry.supported_archs())
+    assert {"ResNetRS50", "ResNetRS101", "GCViTTiny", "GCViTSmall", "convnext_tiny_in22k"} <= set(registry.supported_archs())
     with pytest.raises(ValueError):
-        registry.create_model("convnext_tiny_in22k-200x200", [200, 200], device="cpu")
+        registry.create_model("ResNest50-200x200", [200, 200], device="cpu")
 
 
 def test_scan_checkpoints_errors(tmp_path):

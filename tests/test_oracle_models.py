@@ -39,3 +39,17 @@ def test_gcvit_stage_shapes():
     assert taps["stem"].shape == (1, 56, 56, 64) and taps["level0"].shape == (1, 28, 28, 128)
     assert taps["level1"].shape == (1, 14, 14, 256) and taps["level2"].shape == (1, 7, 7, 512)
     assert taps["level3"].shape == (1, 7, 7, 512) and p.shape == (1, 2)
+
+
+def test_convnext_param_count_and_shapes():
+    """tfimm / timm model card: convnext_tiny 28.59 M parameters with the 1000-class head; the author's stride-2 4x4 stem
+    (models/tfimm/architectures/convnext.py:320-327) turns 200x200 inputs into 99 / 49 / 24 / 12-pixel stages."""
+    from oracle import convnext as C
+
+    W = C.random_weights("tiny", 1000)
+    assert C.param_count(W) == 28_589_128
+    x = np.random.default_rng(0).random((1, 200, 200, 3), dtype=np.float32)
+    taps = {}
+    p = C.forward(x, C.random_weights("tiny", 2), "tiny", taps=taps)
+    assert taps["stem"].shape == (1, 99, 99, 96) and taps["stage1"].shape == (1, 49, 49, 192)
+    assert taps["stage2"].shape == (1, 24, 24, 384) and taps["stage3"].shape == (1, 12, 12, 768) and p.shape == (1, 2)

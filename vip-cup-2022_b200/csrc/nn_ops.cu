@@ -592,6 +592,31 @@ __global__ void scale_cast_fx_bf16_kernel(const long long* __restrict__ x, float
     out[i] = __float2bfloat16_rn(from_fx(x[i]) * scale);
 }
 
+// ---- LayerNormalization of pooled f32 feature vectors [M, C] (ConvNeXt head: GlobalAveragePooling -> LayerNorm -> Dense,
+// models/tfimm/architectures/convnext.py:432-436): one warp per row, two-pass variance, f32 in and out
+__global__ void layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ out, int M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (long long)row * C;
+  float s = 0.0f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float v = 0.0f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    v = fmaf(d, d, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = 1.0f / sqrtf(v / (float)C + eps);
+  for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = fmaf((xr[c] - mean) * rstd, __ldg(gamma + c), __ldg(beta + c));
+}
+
 // ---- row statistics records (stats.cuh; accumulated by the GEMM epilogues with integer atomics) -> (mean, 1 / sigma) per
 // row, the form the folded-LayerNorm consumers load (one coalesced 8-byte load per row and tile)
 __global__ void row_stats_finalize_kernel(const long long* __restrict__ rec, float2* __restrict__ out, long long M, float inv_cols,
@@ -690,6 +715,13 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   VIP_REQUIRE(y && out && C % 8 == 0, VIP_ERR_INVALID, "vip_scale_add_act_bf16: bad argument");
   const long long total8 = (long long)N * HW * (C / 8);
   VIP_LAUNCH((scale_add_act_kernel), grid_for(total8, 256), 256, 0, ST(stream), (const bf16*)y, gate, (const bf16*)shortcut, (bf16*)out, total8, HW, C, act);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, int M, int C, float eps,
+                                 void* stream) {
+  VIP_REQUIRE(x && gamma && beta && out && M > 0 && C > 0, VIP_ERR_INVALID, "vip_layernorm_f32: bad argument");
+  VIP_LAUNCH((layernorm_f32_kernel), (M * 32 + 127) / 128, 128, 0, ST(stream), x, gamma, beta, out, M, C, eps);
   LAUNCH_CHECK();
 }
 

@@ -1,3 +1,4 @@
 """Backbones of the shipped registry (ckpts/ckpts.json of the reference) on the B200 kernels."""
 from .resnet_rs import ResNetRS, ResNetRS50, ResNetRS101, ResNetRS152, ResNetRS200  # noqa: F401
 from .gcvit import GCViT, GCViTBase, GCViTSmall, GCViTTiny, GCViTXTiny, GCViTXXTiny  # noqa: F401,E402
+from .convnext import ConvNeXt  # noqa: F401,E402

@@ -247,6 +247,30 @@ def dwconv3x3(x, w, gelu=False, gap=None):
     return out
 
 
+DW_ACT = {None: 0, "none": 0, "swish": 1, "gelu": 2, "relu": 3}
+
+
+def dwconv(x, w, bias=None, ksize=3, stride=1, pad=None, act=None, gap=None):
+    """Depthwise ksize x ksize convolution on NHWC bf16.  w f32 [k, k, C], bias f32 [C] | None.  ``pad`` = (top, left,
+    bottom, right) explicit zero padding (default: symmetric k // 2); gap as for :func:`dwconv3x3`."""
+    _chk(x, "x"), _chk(w, "w", torch.float32), _chk(bias, "bias", torch.float32), _chk(gap, "gap", STATS)
+    n, h, wd, c = x.shape
+    pt, pl, pb, pr = pad if pad is not None else (ksize // 2,) * 4
+    ho, wo = (h + pt + pb - ksize) // stride + 1, (wd + pl + pr - ksize) // stride + 1
+    out = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_dwconv_bf16(_p(x), _p(w), _p(bias), _p(out), _p(gap), n, h, wd, c, ksize, stride, pt, pl, ho, wo,
+                                          DW_ACT[act], _st()), "vip_dwconv_bf16")
+    return out
+
+
+def layernorm_f32(x, gamma, beta, eps=1e-5):
+    _chk(x, "x", torch.float32), _chk(gamma, "gamma", torch.float32), _chk(beta, "beta", torch.float32)
+    m, c = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().vip_layernorm_f32(_p(x), _p(gamma), _p(beta), _p(out), m, c, float(eps), _st()), "vip_layernorm_f32")
+    return out
+
+
 def maxpool3s2(x):
     _chk(x, "x")
     n, h, w, c = x.shape

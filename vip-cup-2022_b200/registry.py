@@ -25,12 +25,16 @@ def arch_of(model_name: str) -> str:
 
 
 def constructors():
-    from .models import gcvit, resnet_rs
+    from .models import convnext, gcvit, resnet_rs
 
     table = {f"ResNetRS{d}": (lambda d=d, **kw: resnet_rs.ResNetRS(d, **kw)) for d in resnet_rs.BLOCK_ARGS}
     for v in gcvit.CONFIGS:
         pretty = {"xxtiny": "XXTiny", "xtiny": "XTiny", "tiny": "Tiny", "small": "Small", "base": "Base"}[v]
         table[f"GCViT{pretty}"] = (lambda v=v, **kw: gcvit.GCViT(v, **kw))
+    # tfimm registry names (models/tfimm/architectures/convnext.py:440-620): convnext_<size>[_384][_in22k | _in22ft1k]
+    for v in convnext.CONFIGS:
+        for suffix in ("", "_in22k", "_in22ft1k", "_384_in22ft1k"):
+            table[f"convnext_{v}{suffix}"] = (lambda v=v, **kw: convnext.ConvNeXt(v, **kw))
     return table
 
 
