@@ -117,7 +117,8 @@ int vip_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, 
  * row_stats and gap are accumulated: the caller zeroes them (vip_memset_async). */
 typedef struct vip_epilogue {
   const float* bias;      /* [N] or NULL */
-  int act;                /* 0 none, 1 relu, 2 gelu (Keras' erf form evaluated as a fitted tanh: |err| <= 3e-4 |x|), 3 sigmoid */
+  int act;                /* 0 none, 1 relu, 2 gelu (Keras' erf form evaluated as a fitted tanh: |err| <= 3e-4 |x|), 3 sigmoid,
+                             4 swish (x * sigmoid(x)) */
   const float* colscale;  /* [N] or NULL */
   const void* residual;   /* bf16 [M, ldr] or NULL */
   int ldr;

@@ -53,3 +53,23 @@ def test_convnext_param_count_and_shapes():
     p = C.forward(x, C.random_weights("tiny", 2), "tiny", taps=taps)
     assert taps["stem"].shape == (1, 99, 99, 96) and taps["stage1"].shape == (1, 49, 49, 192)
     assert taps["stage2"].shape == (1, 24, 24, 384) and taps["stage3"].shape == (1, 12, 12, 768) and p.shape == (1, 2)
+
+
+def test_efficientnet_param_counts_and_shapes():
+    """kecam model table (efficientnet/__init__.py:80,156): EfficientNetV2T 13.6 M, EfficientNetV1B4 19.3 M trainable
+    parameters (the official EfficientNet-B4 count is 19 341 616); stage shapes of SURVEY.md B.3."""
+    from oracle import efficientnet as E
+
+    for variant, trainable in (("v2t", 13_649_388), ("v1b4", 19_341_616)):
+        W = E.random_weights(variant, 1000)
+        assert sum(a.size for k, a in W.items() if "moving_" not in k) == trainable
+    x = np.random.default_rng(0).random((1, 200, 200, 3), dtype=np.float32)
+    taps = {}
+    E.forward(x, E.random_weights("v2t", 2), "v2t", taps=taps)
+    assert taps["stem"].shape == (1, 100, 100, 24) and taps["stack2"].shape == (1, 25, 25, 48)
+    assert taps["stack4"].shape == (1, 13, 13, 128) and taps["stack5"].shape == (1, 7, 7, 208)
+    x = np.random.default_rng(0).random((1, 224, 224, 3), dtype=np.float32)
+    taps = {}
+    E.forward(x, E.random_weights("v1b4", 2), "v1b4", taps=taps)
+    assert taps["stem"].shape == (1, 112, 112, 48) and taps["stack2"].shape == (1, 28, 28, 56)
+    assert taps["stack6"].shape == (1, 7, 7, 448) and taps["feat"].shape == (1, 1792)

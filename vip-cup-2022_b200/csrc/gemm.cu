@@ -298,6 +298,7 @@ __device__ __forceinline__ void epi_group(float (&v)[8], float rstd, float nmr, 
     if (ACT == ACT_RELU) t = fmaxf(t, 0.0f);
     if (ACT == ACT_GELU) t = gelu_fast(t);
     if (ACT == ACT_SIGMOID) t = 1.0f / (1.0f + __expf(-t));
+    if (ACT == ACT_SWISH) t = t / (1.0f + __expf(-t));   // x * sigmoid(x) (EfficientNet / NFNet activations)
     v[i] = t * sc[i];
   }
 }
@@ -416,6 +417,7 @@ __device__ __forceinline__ void epi_generic32(const uint32_t (&r)[32], uint8_t* 
       case ACT_RELU: epi_group<ACT_RELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
       case ACT_GELU: epi_group<ACT_GELU>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
       case ACT_SIGMOID: epi_group<ACT_SIGMOID>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
+      case ACT_SWISH: epi_group<ACT_SWISH>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
       default: epi_group<ACT_NONE>(v, rstd, nmr, p_colsum, p_bias, p_colscale, n); break;
     }
     uint4* cp = reinterpret_cast<uint4*>(crow + ((cbase16 + q8) ^ swz) * 16);
@@ -1055,7 +1057,7 @@ int pick_bn(long long M, int N, bool deep, bool conv, int num_kb) {
 
 int pick_mode(const GemmEpilogue& e) {
   if (e.row_gate != nullptr) return EPI_SE;
-  if (e.out_bf16 == nullptr || e.colscale != nullptr || e.act == ACT_SIGMOID) return EPI_GENERIC;
+  if (e.out_bf16 == nullptr || e.colscale != nullptr || e.act == ACT_SIGMOID || e.act == ACT_SWISH) return EPI_GENERIC;
   const bool ln = e.ln_stats != nullptr, res = e.residual != nullptr;
   if (res) return (!ln && e.act == ACT_NONE) ? EPI_RES : EPI_GENERIC;
   if (e.row_stats != nullptr) return EPI_GENERIC;

@@ -11,7 +11,7 @@
 
 namespace vip {
 
-enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+enum GemmAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SWISH = 4 };
 
 // Epilogue, applied per output element (m, n) in this order:
 //   v = acc

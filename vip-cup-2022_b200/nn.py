@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import VipError
 
 BF16 = torch.bfloat16
-ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "gelu": 2, "sigmoid": 3}
+ACT = {None: 0, "none": 0, "linear": 0, "relu": 1, "gelu": 2, "sigmoid": 3, "swish": 4}
 
 
 def _p(t):
@@ -134,14 +134,20 @@ def scale_weights(w, gate):
     return out
 
 
-def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, **fused):
+def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, out_hw=None, **fused):
     """x bf16 [N,H,W,C]; w bf16 [Cout, Kp] with K order (r,s,c). Returns bf16 [N,Ho,Wo,Cout].
     1x1 stride 1: plain GEMM on the NHWC activation; C % 8 == 0: implicit GEMM (im2col-mode TMA, nothing materialised);
-    otherwise (the 3-channel network input): explicit im2col matrix + GEMM."""
+    otherwise (the 3-channel network input): explicit im2col matrix + GEMM.  ``out_hw`` (explicit-im2col path only):
+    output size for asymmetric padding -- ``pad`` is then the top / left padding, whatever the output size needs beyond
+    the image at the bottom / right reads as zero (TF 'SAME')."""
     _chk(x, "x"), _chk(w, "w")
     n, h, wd, c = x.shape
     ho = (h + 2 * pad - ksize) // stride + 1
     wo = (wd + 2 * pad - ksize) // stride + 1
+    if out_hw is not None:
+        if c % 8 == 0 and w.shape[1] == ksize * ksize * c:
+            raise VipError("conv2d: out_hw (asymmetric padding) is only supported on the explicit-im2col path")
+        ho, wo = out_hw
     cout = w.shape[0]
     if fused.get("gap") is not None and not fused.get("gap_rows"):
         fused["gap_rows"] = ho * wo
