@@ -147,6 +147,12 @@ int vip_gemm_bf16_ex(const void* A, int lda, const void* B, int ldb, int M, int 
  * models/resnet_rs/resnet_rs_model.py:64-84, model_utils.py:22-46; gcvit layers/feature.py:97-98. */
 int vip_conv2d_bf16(const void* x, int N, int H, int W, int C, const void* w, int ldw, int Cout, int ksize, int stride,
                     int pad, const vip_epilogue_t* epi, void* cuda_stream);
+/* vip_conv2d_bf16 on a channel slice: x points at channel c0 of a wider NHWC tensor whose pixels are ldx channels apart; the
+ * C channels [c0, c0 + C) are convolved.  One call per group makes a grouped convolution (Conv2D(groups=...):
+ * keras_cv_attention_models/nfnets/nfnets.py:150-153, resnest/resnest.py:36-40); the output slice is addressed through
+ * epi->out / epi->ldc in the same way. */
+int vip_conv2d_slice_bf16(const void* x, int N, int H, int W, int C, int ldx, const void* w, int ldw, int Cout, int ksize,
+                          int stride, int pad, const vip_epilogue_t* epi, void* cuda_stream);
 /* cudaMemsetAsync on the caller's stream (zeroing of row_stats / gap accumulators). */
 int vip_memset_async(void* ptr, int value, size_t bytes, void* cuda_stream);
 
@@ -183,6 +189,13 @@ int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap, i
  * EfficientNet MBConv: keras_cv_attention_models/efficientnet/efficientnet_v2.py:80-96 (BN folded by the caller). */
 int vip_dwconv_bf16(const void* x, const float* w, const float* bias, void* out, int64_t* gap, int N, int H, int W, int C,
                     int ksize, int stride, int pad_top, int pad_left, int Ho, int Wo, int act, void* cuda_stream);
+/* out = act(x) * scale over n bf16 elements (n % 8 == 0); act 0 none, 1 relu, 4 swish: the NFNet pre-activation
+ * swish(x) * beta (nfnets/nfnets.py:138). */
+int vip_act_scale_bf16(const void* x, void* out, long long n, int act, float scale, void* cuda_stream);
+/* Efficient Channel Attention gate (common_layers.py:335-353): gate[n, c] = out_scale * sigmoid(sum_k w[k] * mean[n, c + k - ksize/2])
+ * with mean = fixed-point pooled sums (gap) * inv_hw and zeros outside [0, C). */
+int vip_eca_gate_f32(const int64_t* gap, const float* w, float* gate, int N, int C, int ksize, float inv_hw, float out_scale,
+                     void* cuda_stream);
 /* LayerNormalization of pooled f32 vectors [M, C] -> f32 (ConvNeXt head, convnext.py:432-436). */
 int vip_layernorm_f32(const float* x, const float* gamma, const float* beta, float* out, int M, int C, float eps,
                       void* cuda_stream);

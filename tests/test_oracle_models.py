@@ -73,3 +73,16 @@ def test_efficientnet_param_counts_and_shapes():
     E.forward(x, E.random_weights("v1b4", 2), "v1b4", taps=taps)
     assert taps["stem"].shape == (1, 112, 112, 48) and taps["stack2"].shape == (1, 28, 28, 56)
     assert taps["stack6"].shape == (1, 7, 7, 448) and taps["feat"].shape == (1, 1792)
+
+
+def test_eca_nfnet_l0_param_count_and_shapes():
+    """kecam model table (nfnets/__init__.py:82): ECA_NFNetL0 24.14 M parameters; stage shapes of SURVEY.md B.3."""
+    from oracle import nfnet as N
+
+    assert N.param_count(N.random_weights(1000)) == 24_143_872 or abs(N.param_count(N.random_weights(1000)) / 1e6 - 24.14) < 0.01
+    x = np.random.default_rng(0).random((1, 200, 200, 3), dtype=np.float32)
+    taps = {}
+    p = N.forward(x, N.random_weights(2), taps=taps)
+    assert taps["stem"].shape == (1, 50, 50, 128) and taps["stack1"].shape == (1, 50, 50, 256)
+    assert taps["stack2"].shape == (1, 25, 25, 512) and taps["stack3"].shape == (1, 13, 13, 1536)
+    assert taps["stack4"].shape == (1, 7, 7, 1536) and taps["feat"].shape == (1, 2304) and p.shape == (1, 2)

@@ -941,8 +941,9 @@ int make_tmap_2d(CUtensorMap* tm, const void* base, long long rows, int cols, in
 int make_tmap_im2col(CUtensorMap* tm, const void* base, const ConvGeom& c) {
   static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));
   VIP_REQUIRE(fn != nullptr, VIP_ERR_CUDA, "cuTensorMapEncodeIm2col is not available from the driver");
+  const cuuint64_t ld = (cuuint64_t)(c.ldx > 0 ? c.ldx : c.C);
   const cuuint64_t gdim[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.Nimg};
-  const cuuint64_t gstride[3] = {(cuuint64_t)c.C * 2, (cuuint64_t)c.W * c.C * 2, (cuuint64_t)c.H * c.W * c.C * 2};
+  const cuuint64_t gstride[3] = {ld * 2, (cuuint64_t)c.W * ld * 2, (cuuint64_t)c.H * c.W * ld * 2};
   const int lower[2] = {-c.pad, -c.pad};                                        // (W, H)
   const int upper[2] = {c.pad - (c.ksize - 1), c.pad - (c.ksize - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)c.stride, (cuuint32_t)c.stride, 1};
@@ -1220,6 +1221,7 @@ int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* 
   VIP_REQUIRE(c.Ho == (c.H + 2 * c.pad - c.ksize) / c.stride + 1 && c.Wo == (c.W + 2 * c.pad - c.ksize) / c.stride + 1,
               VIP_ERR_INVALID, "conv2d_bf16: Ho/Wo do not match the geometry");
   VIP_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, VIP_ERR_INVALID, "conv2d_bf16: unaligned operand");
+  VIP_REQUIRE(c.ldx == 0 || (c.ldx >= c.C && c.ldx % 8 == 0), VIP_ERR_INVALID, "conv2d_bf16: ldx must be a multiple of 8 and >= C");
   int rc = check_epilogue(epi, Cout);
   if (rc != VIP_OK) return rc;
   GemmArgs g{};
@@ -1265,7 +1267,7 @@ int conv2d_bf16(const __nv_bfloat16* x, const ConvGeom& c, const __nv_bfloat16* 
   // limit, not the TMA mode), so the patch tiles' padding rows are pure loss; the path stays selectable for experiments
   // (VIP_CONV_PATCH=1) and as the base of a halo-reuse variant.
   static const bool patch_env = [] { const char* v = getenv("VIP_CONV_PATCH"); return v != nullptr && v[0] == '1'; }();
-  const bool use_patch = patch_ok && patch_env;
+  const bool use_patch = patch_ok && patch_env && c.ldx == 0;
   CUtensorMap tmA;
   if (!use_patch) {
     rc = make_tmap_im2col(&tmA, x, c);
@@ -1355,6 +1357,17 @@ extern "C" int vip_gemm_grouped_bf16(const void* A, int lda, const void* B, int 
   VIP_REQUIRE(rows_per_group > 0, VIP_ERR_INVALID, "vip_gemm_grouped_bf16: rows_per_group must be positive");
   return vip::gemm_bf16(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(B), ldb,
                         M, N, K, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream), rows_per_group);
+}
+
+extern "C" int vip_conv2d_slice_bf16(const void* x, int N, int H, int W, int C, int ldx, const void* w, int ldw, int Cout,
+                                     int ksize, int stride, int pad, const vip_epilogue_t* epi, void* cuda_stream) {
+  VIP_REQUIRE(x && w && epi && epi->out, VIP_ERR_INVALID, "vip_conv2d_slice_bf16: null pointer");
+  VIP_REQUIRE(stride > 0 && ksize > 0, VIP_ERR_INVALID, "vip_conv2d_slice_bf16: bad kernel / stride");
+  vip::ConvGeom c{N, H, W, C, ksize, stride, pad, 0, 0, ldx};
+  c.Ho = (H + 2 * pad - ksize) / stride + 1;
+  c.Wo = (W + 2 * pad - ksize) / stride + 1;
+  return vip::conv2d_bf16(reinterpret_cast<const __nv_bfloat16*>(x), c, reinterpret_cast<const __nv_bfloat16*>(w), ldw,
+                          Cout, to_epilogue(epi), reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 extern "C" int vip_conv2d_bf16(const void* x, int N, int H, int W, int C, const void* w, int ldw, int Cout, int ksize,

@@ -53,6 +53,8 @@ struct ConvGeom {
   int Nimg, H, W, C;        // input NHWC
   int ksize, stride, pad;   // square kernel, symmetric explicit zero padding
   int Ho, Wo;
+  int ldx = 0;              // channels between consecutive pixels in memory (0 = C): a channel slice [c0, c0 + C) of a wider
+                            // NHWC tensor is convolved by pointing x at channel c0 (grouped convolutions)
 };
 
 // A: [M, K] row-major bf16 (lda elements between rows), B: [N, K] row-major bf16 (ldb).  K, N, lda, ldb, ldc, ldr

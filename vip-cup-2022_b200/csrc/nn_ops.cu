@@ -592,6 +592,41 @@ __global__ void scale_cast_fx_bf16_kernel(const long long* __restrict__ x, float
     out[i] = __float2bfloat16_rn(from_fx(x[i]) * scale);
 }
 
+// ---- out = act(x) * scale (NFNet pre-activation: swish(x) * beta, models/keras_cv_attention_models/nfnets/nfnets.py:138)
+__global__ void act_scale_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long total8, int act, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + i * 8), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = f[k];
+      if (act == 1) v = fmaxf(v, 0.0f);
+      else if (act == 4) v = v / (1.0f + __expf(-v));
+      f[k] = v * scale;
+    }
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
+  }
+}
+
+// ---- Efficient Channel Attention gate (common_layers.py:335-353): pooled means (fixed-point sums * inv_hw) -> zero pad ->
+// Conv1D(k, no bias) along the channel axis -> sigmoid -> * out_scale (the block's attention gain and alpha, nfnets.py:162-168)
+__global__ void eca_gate_kernel(const long long* __restrict__ gap, const float* __restrict__ w, float* __restrict__ gate, int N,
+                                int C, int ksize, float inv_hw, float out_scale) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C, pad = ksize / 2;
+  float s = 0.0f;
+  for (int k = 0; k < ksize; ++k) {
+    const int cc = c + k - pad;
+    if (cc >= 0 && cc < C) s = fmaf(from_fx(gap[(long long)n * C + cc]) * inv_hw, __ldg(w + k), s);
+  }
+  gate[i] = out_scale / (1.0f + __expf(-s));
+}
+
 // ---- LayerNormalization of pooled f32 feature vectors [M, C] (ConvNeXt head: GlobalAveragePooling -> LayerNorm -> Dense,
 // models/tfimm/architectures/convnext.py:432-436): one warp per row, two-pass variance, f32 in and out
 __global__ void layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -715,6 +750,21 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   VIP_REQUIRE(y && out && C % 8 == 0, VIP_ERR_INVALID, "vip_scale_add_act_bf16: bad argument");
   const long long total8 = (long long)N * HW * (C / 8);
   VIP_LAUNCH((scale_add_act_kernel), grid_for(total8, 256), 256, 0, ST(stream), (const bf16*)y, gate, (const bf16*)shortcut, (bf16*)out, total8, HW, C, act);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_act_scale_bf16(const void* x, void* out, long long n, int act, float scale, void* stream) {
+  VIP_REQUIRE(x && out && n > 0 && n % 8 == 0 && (act == 0 || act == 1 || act == 4), VIP_ERR_INVALID,
+              "vip_act_scale_bf16: bad argument (n %% 8 == 0; act 0 none, 1 relu, 4 swish)");
+  VIP_LAUNCH((act_scale_kernel), grid_for(n / 8, 256), 256, 0, ST(stream), (const bf16*)x, (bf16*)out, n / 8, act, scale);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_eca_gate_f32(const int64_t* gap, const float* w, float* gate, int N, int C, int ksize, float inv_hw,
+                                float out_scale, void* stream) {
+  VIP_REQUIRE(gap && w && gate && N > 0 && C > 0 && ksize > 0 && ksize % 2 == 1, VIP_ERR_INVALID, "vip_eca_gate_f32: bad argument");
+  VIP_LAUNCH((eca_gate_kernel), (N * C + 255) / 256, 256, 0, ST(stream), reinterpret_cast<const long long*>(gap), w, gate, N, C,
+             ksize, inv_hw, out_scale);
   LAUNCH_CHECK();
 }
 

@@ -168,6 +168,47 @@ def conv2d(x, w, bias=None, ksize=1, stride=1, pad=0, act=None, residual=None, o
     return y.view(n, ho, wo, cout)
 
 
+def conv2d_grouped(x, ws, biases, ksize=3, stride=1, pad=1, act=None):
+    """Conv2D(groups=G) as G implicit-GEMM convolutions on channel slices: x bf16 [N,H,W,C]; ws[g] bf16 [Cout_g, k*k*C/G]
+    (K order r,s,c); biases[g] f32 [Cout_g] | None.  Returns bf16 [N,Ho,Wo,sum Cout_g]."""
+    _chk(x, "x")
+    n, h, wd, c = x.shape
+    g = len(ws)
+    cg = c // g
+    ho = (h + 2 * pad - ksize) // stride + 1
+    wo = (wd + 2 * pad - ksize) // stride + 1
+    cout = sum(w.shape[0] for w in ws)
+    y = torch.empty((n * ho * wo, cout), dtype=BF16, device=x.device)
+    xe, co0 = x.element_size(), 0
+    for gi, w in enumerate(ws):
+        _chk(w, "w")
+        e = _epilogue(y[:, co0: co0 + w.shape[0]], None if biases is None else biases[gi], act)
+        e.out, e.ldc = y.data_ptr() + co0 * xe, cout
+        rc = _lib.lib().vip_conv2d_slice_bf16(x.data_ptr() + gi * cg * xe, n, h, wd, cg, c, _p(w), w.stride(0), w.shape[0], ksize,
+                                              stride, pad, e, _st())
+        _lib.check(rc, "vip_conv2d_slice_bf16")
+        co0 += w.shape[0]
+    return y.view(n, ho, wo, cout)
+
+
+def act_scale(x, act=None, scale=1.0):
+    """act(x) * scale elementwise (bf16): the NFNet pre-activation swish(x) * beta."""
+    _chk(x, "x")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().vip_act_scale_bf16(_p(x), _p(out), x.numel(), ACT[act], float(scale), _st()), "vip_act_scale_bf16")
+    return out
+
+
+def eca_gate(gap, w, hw, out_scale=1.0):
+    """ECA gate f32 [N,C] from fixed-point pooled sums (int64 [N,C]) and the Conv1D taps w f32 [k]."""
+    _chk(gap, "gap", STATS), _chk(w, "w", torch.float32)
+    n, c = gap.shape
+    gate = torch.empty((n, c), dtype=torch.float32, device=gap.device)
+    _lib.check(_lib.lib().vip_eca_gate_f32(_p(gap), _p(w), _p(gate), n, c, w.numel(), 1.0 / hw, float(out_scale), _st()),
+               "vip_eca_gate_f32")
+    return gate
+
+
 def pair_rows_weights(w, bias):
     """For ``conv2d_paired``: [Cout, 32] (K padded to 32) -> block-diagonal bf16 [2 Cout, 64] and the duplicated bias."""
     cout, kp = w.shape
