@@ -189,6 +189,12 @@ int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap, i
  * EfficientNet MBConv: keras_cv_attention_models/efficientnet/efficientnet_v2.py:80-96 (BN folded by the caller). */
 int vip_dwconv_bf16(const void* x, const float* w, const float* bias, void* out, int64_t* gap, int N, int H, int W, int C,
                     int ksize, int stride, int pad_top, int pad_left, int Ho, int Wo, int act, void* cuda_stream);
+/* ResNeSt split attention, radix 2 (keras_cv_attention_models/resnest/resnest.py:16-24,57-62): x bf16 [N, HW, 2F] (the two
+ * radix splits side by side), logits f32 [N, 2F]; a = softmax over the radix per channel;
+ * out[n, p, c] = a0[n, c] x[n, p, c] + a1[n, c] x[n, p, F + c], bf16 [N, HW, F]. */
+int vip_split_attention2_bf16(const void* x, const float* logits, void* out, int N, int HW, int F, void* cuda_stream);
+/* ZeroPadding2D(1) + AveragePooling2D(3, strides 2): the padded zeros count (divisor 9), resnest.py:63-65. */
+int vip_avgpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* cuda_stream);
 /* out = act(x) * scale over n bf16 elements (n % 8 == 0); act 0 none, 1 relu, 4 swish: the NFNet pre-activation
  * swish(x) * beta (nfnets/nfnets.py:138). */
 int vip_act_scale_bf16(const void* x, void* out, long long n, int act, float scale, void* cuda_stream);

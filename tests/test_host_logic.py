@@ -53,7 +53,7 @@ def test_config_and_registry():
     assert 8 * registry.NAME2BS.get("ResNetRS50-200x200", 16) == 128      # main.py:85
     assert {"ResNetRS50", "ResNetRS101", "GCViTTiny", "GCViTSmall", "convnext_tiny_in22k"} <= set(registry.supported_archs())
     with pytest.raises(ValueError):
-        registry.create_model("ResNest50-200x200", [200, 200], device="cpu")
+        registry.create_model("HorNetBase-200x200", [200, 200], device="cpu")   # named in NAME2BS, not in ckpts.json
 
 
 def test_scan_checkpoints_errors(tmp_path):

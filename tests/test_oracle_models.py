@@ -86,3 +86,16 @@ def test_eca_nfnet_l0_param_count_and_shapes():
     assert taps["stem"].shape == (1, 50, 50, 128) and taps["stack1"].shape == (1, 50, 50, 256)
     assert taps["stack2"].shape == (1, 25, 25, 512) and taps["stack3"].shape == (1, 13, 13, 1536)
     assert taps["stack4"].shape == (1, 7, 7, 1536) and taps["feat"].shape == (1, 2304) and p.shape == (1, 2)
+
+
+def test_resnest50_param_count_and_shapes():
+    """ResNeSt-50: 27.48 M trainable parameters (the published count of the architecture); stage shapes of SURVEY.md B.3."""
+    from oracle import resnest as R
+
+    assert abs(R.param_count(R.random_weights(1000), trainable_only=True) / 1e6 - 27.48) < 0.01
+    x = np.random.default_rng(0).random((1, 200, 200, 3), dtype=np.float32)
+    taps = {}
+    p = R.forward(x, R.random_weights(2), taps=taps)
+    assert taps["stem"].shape == (1, 50, 50, 64) and taps["stack1"].shape == (1, 50, 50, 256)
+    assert taps["stack2"].shape == (1, 25, 25, 512) and taps["stack3"].shape == (1, 13, 13, 1024)
+    assert taps["stack4"].shape == (1, 7, 7, 2048) and p.shape == (1, 2)

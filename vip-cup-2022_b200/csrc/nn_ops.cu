@@ -592,6 +592,63 @@ __global__ void scale_cast_fx_bf16_kernel(const long long* __restrict__ x, float
     out[i] = __float2bfloat16_rn(from_fx(x[i]) * scale);
 }
 
+// ---- ResNeSt split attention, radix 2 (keras_cv_attention_models/resnest/resnest.py:16-24, 57-62): r-softmax of the
+// attention logits over the two radix splits, then out[n, p, c] = a0[n, c] x[n, p, c] + a1[n, c] x[n, p, F + c]
+__global__ void split_attention2_kernel(const bf16* __restrict__ x, const float* __restrict__ logits, bf16* __restrict__ out,
+                                        long long total8, int HW, int F) {
+  pdl_trigger();
+  pdl_wait();
+  const int f8n = F >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int f8 = (int)(i % f8n);
+    const long long pix = i / f8n;
+    const int n = (int)(pix / HW);
+    const float* lg = logits + (long long)n * 2 * F + f8 * 8;
+    float x0[8], x1[8], o[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + pix * 2 * F + f8 * 8), x0);
+    unpack8(*reinterpret_cast<const bf16x8*>(x + pix * 2 * F + F + f8 * 8), x1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float z0 = __ldg(lg + k), z1 = __ldg(lg + F + k);
+      const float a0 = 1.0f / (1.0f + __expf(z1 - z0));     // softmax over the two radix logits
+      o[k] = fmaf(a0, x0[k], (1.0f - a0) * x1[k]);
+    }
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(o);
+  }
+}
+
+// ---- ZeroPadding2D(1) + AveragePooling2D(3, strides=2) (resnest.py:63-65): the padded zeros count, divisor 9
+__global__ void avgpool3s2_zeropad_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int Ho,
+                                          int Wo) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8n = C >> 3;
+  const long long total = (long long)N * Ho * Wo * c8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    long long t = i / c8n;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho), n = (int)(t / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * H + iy) * W + ix) * C + c8 * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= (1.0f / 9.0f);
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(acc);
+  }
+}
+
 // ---- out = act(x) * scale (NFNet pre-activation: swish(x) * beta, models/keras_cv_attention_models/nfnets/nfnets.py:138)
 __global__ void act_scale_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long total8, int act, float scale) {
   pdl_trigger();
@@ -750,6 +807,22 @@ extern "C" int vip_scale_add_act_bf16(const void* y, const float* gate, const vo
   VIP_REQUIRE(y && out && C % 8 == 0, VIP_ERR_INVALID, "vip_scale_add_act_bf16: bad argument");
   const long long total8 = (long long)N * HW * (C / 8);
   VIP_LAUNCH((scale_add_act_kernel), grid_for(total8, 256), 256, 0, ST(stream), (const bf16*)y, gate, (const bf16*)shortcut, (bf16*)out, total8, HW, C, act);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_split_attention2_bf16(const void* x, const float* logits, void* out, int N, int HW, int F, void* stream) {
+  VIP_REQUIRE(x && logits && out && N > 0 && HW > 0 && F > 0 && F % 8 == 0, VIP_ERR_INVALID,
+              "vip_split_attention2_bf16: bad argument (F %% 8 == 0)");
+  const long long total8 = (long long)N * HW * (F / 8);
+  VIP_LAUNCH((split_attention2_kernel), grid_for(total8, 256), 256, 0, ST(stream), (const bf16*)x, logits, (bf16*)out, total8, HW, F);
+  LAUNCH_CHECK();
+}
+
+extern "C" int vip_avgpool3s2_bf16(const void* x, void* out, int N, int H, int W, int C, void* stream) {
+  VIP_REQUIRE(x && out && C % 8 == 0, VIP_ERR_INVALID, "vip_avgpool3s2_bf16: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  VIP_LAUNCH((avgpool3s2_zeropad_kernel), grid_for((long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST(stream), (const bf16*)x,
+             (bf16*)out, N, H, W, C, Ho, Wo);
   LAUNCH_CHECK();
 }
 

@@ -4,3 +4,4 @@ from .gcvit import GCViT, GCViTBase, GCViTSmall, GCViTTiny, GCViTXTiny, GCViTXXT
 from .convnext import ConvNeXt  # noqa: F401,E402
 from .efficientnet import EfficientNet  # noqa: F401,E402
 from .nfnet import ECANFNetL0  # noqa: F401,E402
+from .resnest import ResNeSt50  # noqa: F401,E402

@@ -191,6 +191,24 @@ def conv2d_grouped(x, ws, biases, ksize=3, stride=1, pad=1, act=None):
     return y.view(n, ho, wo, cout)
 
 
+def split_attention2(x, logits):
+    """Radix-2 split attention: x bf16 [N,H,W,2F], logits f32 [N,2F] -> bf16 [N,H,W,F] (r-softmax weighted sum of the halves)."""
+    _chk(x, "x"), _chk(logits, "logits", torch.float32)
+    n, h, w, c2 = x.shape
+    out = torch.empty((n, h, w, c2 // 2), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_split_attention2_bf16(_p(x), _p(logits), _p(out), n, h * w, c2 // 2, _st()), "vip_split_attention2_bf16")
+    return out
+
+
+def avgpool3s2(x):
+    """ZeroPadding2D(1) + AveragePooling2D(3, strides=2), divisor 9."""
+    _chk(x, "x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=BF16, device=x.device)
+    _lib.check(_lib.lib().vip_avgpool3s2_bf16(_p(x), _p(out), n, h, w, c, _st()), "vip_avgpool3s2_bf16")
+    return out
+
+
 def act_scale(x, act=None, scale=1.0):
     """act(x) * scale elementwise (bf16): the NFNet pre-activation swish(x) * beta."""
     _chk(x, "x")

@@ -25,7 +25,7 @@ def arch_of(model_name: str) -> str:
 
 
 def constructors():
-    from .models import convnext, efficientnet, gcvit, nfnet, resnet_rs
+    from .models import convnext, efficientnet, gcvit, nfnet, resnest, resnet_rs
 
     table = {f"ResNetRS{d}": (lambda d=d, **kw: resnet_rs.ResNetRS(d, **kw)) for d in resnet_rs.BLOCK_ARGS}
     for v in gcvit.CONFIGS:
@@ -39,6 +39,7 @@ def constructors():
     table["EfficientNetV2T"] = lambda **kw: efficientnet.EfficientNet("v2t", **kw)
     table["EfficientNetV1B4"] = lambda **kw: efficientnet.EfficientNet("v1b4", **kw)
     table["ECA_NFNetL0"] = lambda **kw: nfnet.ECANFNetL0(**kw)                        # nfnets/nfnets.py:316-320
+    table["ResNest50"] = lambda **kw: resnest.ResNeSt50(**kw)                          # resnest/resnest.py:76-77
     return table
 
 
@@ -55,7 +56,7 @@ def create_model(model_name, dim, num_classes=2, head_act="softmax", device="cud
     if arch.startswith("ResNetRS"):
         return table[arch](input_shape=(dim[0], dim[1], 3), classes=num_classes, classifier_activation=head_act,
                            device=device)
-    if arch.startswith("EfficientNet") or arch.startswith("ECA_NFNet"):
+    if arch.startswith("EfficientNet") or arch.startswith("ECA_NFNet") or arch.startswith("ResNest"):
         return table[arch](input_shape=(dim[0], dim[1], 3), num_classes=num_classes, classifier_activation=head_act,
                            device=device)
     return table[arch](input_shape=(dim[0], dim[1], 3), num_classes=num_classes, head_act=head_act, device=device)
