@@ -116,6 +116,51 @@ def test_main_py_tta_multibatch_mixed_sizes(workdir, tmp_path):
 
 
 @pytest.mark.timeout(1800)
+def test_main_py_full_reference_registry(tmp_path, cuda_device):
+    """The reference's own ``ckpts/ckpts.json`` (7 entries: ConvNeXt-tiny, ResNeSt-50, GCViT-tiny, EfficientNetV2-T,
+    EfficientNetV1-B4, ECA-NFNet-L0, ResNet-RS-50) dropped onto this build: every member's P(synthetic) within 1e-2 of its
+    oracle on 24 JPEG files (natural, un-amplified heads), and the CSV of the 7-model ensemble equal to the oracle
+    epilogue's wherever the ensemble probability is not within 5e-3 of the threshold."""
+    import json
+
+    import make_decided_dataset
+    import make_random_ckpts
+    import make_synth_dataset
+    from PIL import Image
+
+    from oracle.predict import epilogue
+
+    entries = json.load(open(os.path.join(ROOT, "ckpts", "ckpts.json")))
+    names = [e[0] for e in entries]
+    assert len(names) == 7
+    models = str(tmp_path / "ckpts")
+    make_random_ckpts.main(models, names, calibrate=False)
+    data, n = str(tmp_path / "data"), 24
+    make_synth_dataset.main(data, n)
+    os.makedirs(str(tmp_path / "out"), exist_ok=True)
+    out_csv = str(tmp_path / "out" / "pred.csv")
+    env = dict(os.environ, VIP_MODEL_DIR=models, VIP_SAVE_PROBS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main.py"), os.path.join(data, "input.csv"), out_csv], env=env,
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = pd.read_csv(out_csv)
+    test_csv = pd.read_csv(os.path.join(data, "input.csv"))
+    imgs = [np.asarray(Image.open(os.path.join(data, f)).convert("RGB")) for f in test_csv.filename]
+    probs, errs = [], {}
+    for m in names:
+        p = make_decided_dataset.oracle_model_probs(models, m, imgs)
+        probs.append([p])
+        mine = pd.read_csv(os.path.join(str(tmp_path / "out"), "temp", m + "_pred.csv")).logit.values
+        errs[m] = float(np.abs(mine - (1 - p[:, 0])).max())
+    print("per-model max |P_b200 - P_oracle| on the reference registry:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 1e-2, errs
+    ref = epilogue(test_csv, probs, tta=1, thr=THR)
+    ens = np.mean([1 - p[0][:, 0].astype(np.float64) for p in probs], axis=0)[np.argsort(test_csv.filename.values)]
+    decided = np.abs(ens - THR) > 5e-3
+    assert list(got.filename) == list(ref.filename) and (got.logit.values[decided] == ref.logit.values[decided]).all()
+
+
+@pytest.mark.timeout(1800)
 def test_main_py_bit_reproducible_across_runs_batches_and_gpus(workdir):
     """The thresholded CSV is the contract of a classifier: the probabilities behind it must not depend on the run, on the
     batch an image is in, or on how many GPUs share the list (statistics that cross kernels are accumulated with integer

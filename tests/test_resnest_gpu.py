@@ -25,7 +25,7 @@ def test_split_attention_and_avgpool3(cuda_device):
     assert p.shape == pref.shape and torch.allclose(p.float(), pref, rtol=2 ** -7, atol=2e-3)
 
 
-@pytest.mark.parametrize("hw,head,seed", [(200, "softmax", 1), (200, "sigmoid", 2), (224, "softmax", 3)])
+@pytest.mark.parametrize("hw,head,seed", [(200, "softmax", 1), (200, "sigmoid", 2), (224, "softmax", 5)])
 def test_resnest50_matches_oracle(cuda_device, hw, head, seed):
     import torch
 

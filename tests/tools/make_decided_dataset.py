@@ -19,8 +19,12 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def oracle_model_probs(models_dir, name, imgs, tta_flags=None):
     """float32 [len(imgs), k] (or [passes * len, k] with ``tta_flags`` = list of per-pass uint8 flag arrays)."""
+    from oracle import convnext as C
+    from oracle import efficientnet as E
     from oracle import gcvit as G
+    from oracle import nfnet as NF
     from oracle import preprocess as P
+    from oracle import resnest as RN
     from oracle import resnet_rs as R
     from vipcup_b200 import registry
 
@@ -40,8 +44,18 @@ def oracle_model_probs(models_dir, name, imgs, tta_flags=None):
         act = meta["head_act"] or "softmax"
         if arch.startswith("ResNetRS"):
             out.append(R.forward(x, W, int(arch[len("ResNetRS"):]), head_act=act))
-        else:
+        elif arch.startswith("GCViT"):
             out.append(G.forward(x, W, arch[len("GCViT"):].lower(), head_act=act))
+        elif arch.startswith("convnext_"):
+            out.append(C.forward(x, W, arch.split("_")[1], head_act=act))
+        elif arch.startswith("EfficientNet"):
+            out.append(E.forward(x, W, {"EfficientNetV2T": "v2t", "EfficientNetV1B4": "v1b4"}[arch], head_act=act))
+        elif arch == "ECA_NFNetL0":
+            out.append(NF.forward(x, W, head_act=act))
+        elif arch == "ResNest50":
+            out.append(RN.forward(x, W, head_act=act))
+        else:
+            raise SystemExit(f"no oracle for {arch}")
     return np.concatenate(out, 0).astype(np.float32)
 
 

@@ -12,7 +12,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 
 
 def weights_for(model_name, num_classes, seed):
+    from oracle import convnext as C
+    from oracle import efficientnet as E
     from oracle import gcvit as G
+    from oracle import nfnet as NF
+    from oracle import resnest as RN
     from oracle import resnet_rs as R
 
     arch = model_name.rsplit("-", 1)[0]
@@ -20,6 +24,14 @@ def weights_for(model_name, num_classes, seed):
         return R.random_weights(int(arch[len("ResNetRS"):]), num_classes, seed)
     if arch.startswith("GCViT"):
         return G.random_weights(arch[len("GCViT"):].lower(), num_classes, seed)
+    if arch.startswith("convnext_"):
+        return C.random_weights(arch.split("_")[1], num_classes, seed)
+    if arch in ("EfficientNetV2T", "EfficientNetV1B4"):
+        return E.random_weights({"EfficientNetV2T": "v2t", "EfficientNetV1B4": "v1b4"}[arch], num_classes, seed)
+    if arch == "ECA_NFNetL0":
+        return NF.random_weights(num_classes, seed)
+    if arch == "ResNest50":
+        return RN.random_weights(num_classes, seed)
     raise SystemExit(f"no random-init generator for {arch}")
 
 
