@@ -247,6 +247,51 @@ int vip_mlp_fused_bf16(const void* x, const void* x_lo, long long M, int C, int 
  * resnet_rs_model.py:149) */
 int vip_scale_cast_fx_bf16(const int64_t* x, float scale, void* out, long long n, void* cuda_stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * JPEG decode on the device.  Replaces tf.io.read_file -> tf.image.decode_jpeg(channels=3) of
+ * dataset/dataset.py:24-28 (libjpeg-turbo defaults: JDCT_ISLOW, fancy chroma upsampling) for baseline
+ * sequential Huffman files; results are bit-identical to libjpeg-turbo's (tests compare with Pillow).
+ *
+ * Flow: the caller reads the files, vip_jpeg_parse (HOST, no GPU) fills one descriptor per file, vip_jpeg_plan
+ * assigns every image its slice of the output / coefficient buffers, the caller copies the concatenated file
+ * bytes and the descriptors to the device, and vip_jpeg_decode runs two kernels: entropy decode (one warp per
+ * image; lane 0 walks the Huffman stream, the warp stores each 8x8 block of coefficients with one coalesced
+ * write) and dequantise -> integer IDCT -> fancy upsample -> YCbCr->RGB (8 lanes per block).
+ * Files the kernels do not cover (progressive, arithmetic, 12-bit, CMYK / RGB colour spaces, sampling other than
+ * 4:4:4 / 4:2:2 / 4:2:0 / grey, multi-scan) get status != 0 from the parser; the caller decodes those on the host
+ * (libjpeg through Pillow, i.e. what the reference's CPU path does) into the same output slice. */
+#define VIP_JPEG_OK 0
+#define VIP_JPEG_NOT_JPEG 1      /* no SOI / truncated header */
+#define VIP_JPEG_UNSUPPORTED 2   /* valid JPEG outside the subset above */
+typedef struct vip_jpeg_desc {
+  int32_t status;            /* VIP_JPEG_* (parser) */
+  int32_t width, height;     /* image size; valid whenever a frame header was read, even if status != 0 */
+  int32_t ncomp;             /* 1 (grey) or 3 (YCbCr) */
+  int32_t hs[3], vs[3];      /* sampling factors per component */
+  int32_t tq[3], td[3], ta[3]; /* quantisation / DC Huffman / AC Huffman table selectors per component */
+  int32_t restart_interval;  /* MCUs between RSTn markers, 0 = none */
+  int32_t scan_offset;       /* first byte of the entropy-coded segment inside the file */
+  int32_t scan_bytes;        /* its length (up to the marker that ends the scan) */
+  int64_t file_offset;       /* CALLER: offset of this file's first byte in the device byte buffer */
+  int64_t dst_offset;        /* vip_jpeg_plan: byte offset of this image's [height, width, 3] u8 pixels in dst */
+  int64_t coef_offset;       /* vip_jpeg_plan: first 8x8 block of this image in the coefficient workspace */
+  uint16_t qt[4][64];        /* quantisation tables, natural (row-major) order */
+  uint8_t huff_bits[4][16];  /* code-length counts: tables 0,1 = DC 0,1; 2,3 = AC 0,1 */
+  uint8_t huff_vals[4][256]; /* symbols in code order */
+} vip_jpeg_desc;
+/* HOST: parse the headers of one JPEG file (no pixel work).  Returns VIP_OK and sets desc->status; a file that is not a
+ * decodable JPEG is not an error of this call. */
+int vip_jpeg_parse(const uint8_t* file, size_t len, vip_jpeg_desc* desc);
+/* HOST: assign dst_offset / coef_offset of N descriptors (dense, in order; every image with a known size gets an output
+ * slice, decodable ones also a coefficient slice).  Writes the total bytes of dst and the number of int16[64] blocks. */
+int vip_jpeg_plan(vip_jpeg_desc* descs, int N, int64_t* dst_bytes, int64_t* coef_blocks);
+/* DEVICE: decode the images with status == 0.  data = device byte buffer holding the files; descs_host / descs_dev = the
+ * same N descriptors in host and device memory; coef = device workspace of coef_blocks * 64 int16; dst = device u8
+ * buffer of dst_bytes (interleaved RGB, rows tightly packed); err = device int32 [N] or NULL, set to 1 for an image whose
+ * entropy-coded data is corrupt (ran out of data / invalid code), 0 otherwise. */
+int vip_jpeg_decode(const uint8_t* data, const vip_jpeg_desc* descs_host, const vip_jpeg_desc* descs_dev, int N,
+                    int16_t* coef, uint8_t* dst, int32_t* err, void* cuda_stream);
+
 /* Exhaustive on-device self check of the exact x/255 sequence used by the kernels against IEEE division
  * (dataset/dataset.py:37).  Writes the number of mismatching bit patterns to *mismatches. */
 int vip_selftest_div255(uint64_t* mismatches, void* cuda_stream);

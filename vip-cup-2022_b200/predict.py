@@ -113,7 +113,10 @@ class GraphedModel:
 
 def _load_model(model_name, model_path, dim, device):
     W, meta = registry.load_checkpoint(model_path)
-    head_k = W["predictions/kernel" if "predictions/kernel" in W else "head/kernel"].shape[1]
+    head_key = next((k for k in ("predictions/kernel", "head/kernel", "head/fc/kernel") if k in W), None)
+    if head_key is None:
+        raise ValueError(f"{model_path}: no classifier kernel (predictions/kernel, head/kernel, head/fc/kernel) in the checkpoint")
+    head_k = W[head_key].shape[1]
     model = registry.create_model(model_name, dim, num_classes=head_k,
                                   head_act=meta["head_act"] or ("sigmoid" if head_k == 1 else "softmax"), device=device)
     return model.load_weights(W)
