@@ -277,6 +277,8 @@ def _h2v2_fancy_upsample(c: np.ndarray) -> np.ndarray:
     (jdmainct context rows). Returns [2*hc, 2*wc]."""
     c = c.astype(np.int64)
     hc, wc = c.shape
+    if wc <= 2:    # jdsample.c jinit_upsampler: fancy upsampling needs downsampled_width > 2, else plain replication
+        return np.repeat(np.repeat(c, 2, axis=0), 2, axis=1)
     up = np.concatenate([c[:1], c[:-1]], axis=0)     # row above (replicated at top)
     dn = np.concatenate([c[1:], c[-1:]], axis=0)     # row below (replicated at bottom)
     rows = np.empty((2 * hc, wc), dtype=np.int64)

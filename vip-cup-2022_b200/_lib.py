@@ -75,6 +75,9 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "vip_cast_f32_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "vip_selftest_div255": (C.c_int, [C.POINTER(C.c_uint64), C.c_void_p]),
+    "vip_jpeg_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),
+    "vip_jpeg_plan": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "vip_jpeg_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -419,6 +419,8 @@ __global__ void __launch_bounds__(kPixThreads) jpeg_pixels_kernel(const vip_jpeg
         ch[comp][0][1] = (3 * u_c + u_r + 7) >> 4;
         ch[comp][1][0] = (3 * d_c + d_l + 8) >> 4;
         ch[comp][1][1] = (3 * d_c + d_r + 7) >> 4;
+        // jdsample.c jinit_upsampler: planes of one or two samples per row are replicated (h2v2_upsample), not interpolated
+        if (wc <= 2) ch[comp][0][0] = ch[comp][0][1] = ch[comp][1][0] = ch[comp][1][1] = n_c;
       }
       const int nx = (2 * cx + 1 < W) ? 2 : 1;
 #pragma unroll
@@ -453,8 +455,9 @@ __global__ void __launch_bounds__(kPixThreads) jpeg_pixels_kernel(const vip_jpeg
         const int b0 = PB[y * pitch[1] + cx], r0 = PR[y * pitch[2] + cx];
         const int cbl = (3 * b0 + PB[y * pitch[1] + cxm] + 1) >> 2, cbr = (3 * b0 + PB[y * pitch[1] + cxp] + 2) >> 2;
         const int crl = (3 * r0 + PR[y * pitch[2] + cxm] + 1) >> 2, crr = (3 * r0 + PR[y * pitch[2] + cxp] + 2) >> 2;
-        ycc_to_rgb(PY[y * pitch[0] + 2 * cx], cbl, crl, px);
-        ycc_to_rgb(PY[y * pitch[0] + 2 * cx + 1], cbr, crr, px + 3);
+        const bool fancy = wp > 2;      // jinit_upsampler: h2v1_upsample (replication) for planes of one or two samples per row
+        ycc_to_rgb(PY[y * pitch[0] + 2 * cx], fancy ? cbl : b0, fancy ? crl : r0, px);
+        ycc_to_rgb(PY[y * pitch[0] + 2 * cx + 1], fancy ? cbr : b0, fancy ? crr : r0, px + 3);
       }
       store_rgb_pair(img + ((size_t)y * W + 2 * cx) * 3, px, nx);
     }

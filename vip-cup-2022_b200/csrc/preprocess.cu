@@ -461,6 +461,8 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
         ch[comp][0][1] = (3 * u_c + u_r + 7) >> 4;
         ch[comp][1][0] = (3 * d_c + d_l + 8) >> 4;
         ch[comp][1][1] = (3 * d_c + d_r + 7) >> 4;
+        // jdsample.c jinit_upsampler: planes of one or two samples per row are replicated (h2v2_upsample), not interpolated
+        if (wc <= 2) ch[comp][0][0] = ch[comp][0][1] = ch[comp][1][0] = ch[comp][1][1] = n_c;
       }
       float fv[2][2][3];
 #pragma unroll

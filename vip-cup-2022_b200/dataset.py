@@ -1,10 +1,12 @@
 """Data pipeline with the surface of the reference's ``dataset/dataset.py`` (seeding 12-17, build_decoder 22-48,
 build_augmenter 50-59, build_dataset 64-102).
 
-What changed underneath: tf.io.read_file / tf.image.decode_jpeg run on host threads through Pillow (the same
-libjpeg-turbo defaults TF uses: ISLOW IDCT, fancy upsampling) into pinned uint8 staging buffers; everything after the
-decode -- cast, bicubic resize, /255, the augmentations -- is ONE fused CUDA kernel (vip_preprocess) that writes the
-[B,H,W,3] batch in device memory, where the backbones consume it.  tf.data's RNG stream cannot be reproduced, so
+What changed underneath: tf.io.read_file stays on host threads; tf.image.decode_jpeg runs ON THE DEVICE for baseline JPEG
+files (vip_jpeg_decode: Huffman decode, integer IDCT, fancy upsampling, colour conversion, bit-identical to libjpeg-turbo;
+the host only walks the marker segments) and through Pillow on host threads (the same libjpeg-turbo defaults TF uses:
+ISLOW IDCT, fancy upsampling) for everything else (progressive files, PNG, a caller-supplied decode_fn, VIP_JPEG_DEVICE=0);
+everything after the decode -- cast, bicubic resize, /255, the augmentations -- is ONE fused CUDA kernel (vip_preprocess)
+that writes the [B,H,W,3] batch in device memory, where the backbones consume it.  tf.data's RNG stream cannot be reproduced, so
 the TTA decisions of apply_augment (dataset/augment.py:153-182: p=0.8 gate, hflip 0.5, vflip 0.5, gray 0.3) are drawn from
 a counter-based Philox-4x32-10 keyed by CFG.seed and indexed by (image position, TTA pass) -- independent of batching and
 sharding -- and passed to the kernel as explicit per-image flags."""
@@ -17,7 +19,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
-from . import ops
+from . import jpeg, ops
 
 
 def seeding(CFG):
@@ -40,6 +42,8 @@ def build_decoder(with_labels, img_size, CFG, ext="jpg"):
 
         with Image.open(path) as im:
             return np.asarray(im.convert("RGB"))
+
+    decode.device_decodable = ext in ("jpg", "jpeg")   # DeviceDataset may hand the file bytes to vip_jpeg_decode instead
 
     def decode_with_labels(path, label):
         return decode(path), label
@@ -95,6 +99,16 @@ def build_augmenter(with_labels=True, img_size=(200, 200), CFG=None):
     return augment
 
 
+class RawJpegs(list):
+    """One batch of undecoded files: a list of (file bytes, parsed descriptor); the device decode is memoised so that every
+    model of the ensemble consumes the same decoded pixels."""
+
+    def decoded(self, device):
+        if getattr(self, "_decoded", None) is None:
+            self._decoded = jpeg.decode_batch([f for f, _ in self], [d for _, d in self], device=device)
+        return self._decoded
+
+
 class DeviceDataset:
     """Iterable of device batches [B,H,W,3] (bf16 by default).  ``repeat`` / ``steps`` semantics of tf.data are
     replaced by explicit passes: iterating yields ceil(N/B) batches of one pass; call again for the next TTA pass."""
@@ -105,6 +119,8 @@ class DeviceDataset:
         self.index_offset, self.passes_done = int(index_offset), 0   # position of paths[0] in the whole list; TTA pass counter
         self.decode_fn, self.augment_fn, self.augment = decode_fn, augment_fn, augment
         self.out_dtype, self.device = out_dtype, device
+        # JPEG decode on the device unless the caller brought a decoder of its own or switched it off
+        self.device_decode = (getattr(decode_fn, "device_decodable", False) and os.environ.get("VIP_JPEG_DEVICE", "1") != "0")
         self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
         # the prefetch task waits for the decode tasks: it needs a thread of its own (a single-worker pool would deadlock)
         self.prefetcher = ThreadPoolExecutor(max_workers=1)
@@ -113,12 +129,14 @@ class DeviceDataset:
         return -(-len(self.paths) // self.batch_size)
 
     def _decode_batch(self, paths):
+        if self.device_decode:
+            return RawJpegs(self.pool.map(jpeg.read_and_parse, paths))     # file read + marker walk only
         imgs = list(self.pool.map(self.decode_fn, paths))
         return imgs
 
     def host_batches(self, depth=2):
-        """One pass over the images as (first index, [decoded uint8 HxWx3 arrays]) per batch; the next ``depth`` batches
-        are being decoded on the thread pool while the caller works on the current one (tf.data prefetch,
+        """One pass over the images as (first index, [decoded uint8 HxWx3 arrays] or RawJpegs) per batch; the next ``depth``
+        batches are being read / decoded on the thread pool while the caller works on the current one (tf.data prefetch,
         dataset/dataset.py:100)."""
         n = len(self.paths)
         starts = list(range(0, n, self.batch_size))
@@ -142,7 +160,11 @@ class DeviceDataset:
 
     def stage(self, imgs):
         """Decoded images of ONE size -> pinned uint8 [n,Hs,Ws,3] -> device (async copy on the current stream); None when
-        the sizes differ (the caller then takes the per-size path of ``to_device``)."""
+        the sizes differ (the caller then takes the per-size path of ``to_device``).  Undecoded files: H2D of the file
+        bytes and the two decode kernels instead."""
+        if isinstance(imgs, RawJpegs):
+            dec = imgs.decoded(self.device)
+            return dec.stacked() if dec.uniform_shape() is not None else None
         shape = imgs[0].shape
         if any(im.shape != shape for im in imgs):
             return None
@@ -156,14 +178,18 @@ class DeviceDataset:
     def _to_device(self, imgs, flags, img_size=None):
         h, w = img_size or self.img_size
         out = torch.empty((len(imgs), h, w, 3), dtype=self.out_dtype, device=self.device)
+        dec = imgs.decoded(self.device) if isinstance(imgs, RawJpegs) else None
         # group by decoded size (test images may have other dimensions, dataset.py:32-34)
         groups = {}
-        for i, im in enumerate(imgs):
-            groups.setdefault(im.shape[:2], []).append(i)
+        for i in range(len(imgs)):
+            groups.setdefault(tuple(dec.layout[i][1:3]) if dec is not None else imgs[i].shape[:2], []).append(i)
         for (hs, ws), idx in groups.items():
-            stage = torch.empty((len(idx), hs, ws, 3), dtype=torch.uint8).pin_memory()
-            np.stack([imgs[i] for i in idx], out=stage.numpy())
-            src = stage.to(self.device, non_blocking=True)
+            if dec is not None:
+                src = dec.stacked() if len(groups) == 1 else torch.stack([dec.image(i) for i in idx])
+            else:
+                stage = torch.empty((len(idx), hs, ws, 3), dtype=torch.uint8).pin_memory()
+                np.stack([imgs[i] for i in idx], out=stage.numpy())
+                src = stage.to(self.device, non_blocking=True)
             fl = None
             if flags is not None:
                 fl = torch.from_numpy(np.ascontiguousarray(flags[idx])).to(self.device)
