@@ -333,6 +333,71 @@ def bench_preprocess_nojpeg(dev, steps, hbm_peak):
     return out
 
 
+def bench_jpeg_decode(dev, steps, hbm_peak):
+    """Device JPEG decode (dataset/dataset.py:24-28): 1024 synthetic 200x200 4:2:0 files (the config-4 file
+    generator) -> u8 [1024,200,200,3].  Kernel-only time (files resident in HBM) and the whole ``decode_batch`` call from
+    host bytes (pinned staging + H2D + kernels), both with CUDA events; the host libjpeg rate on the same files beside it."""
+    import ctypes as C
+    import io
+    import tempfile
+
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from vipcup_b200 import _lib, jpeg
+
+    n, unique = 1024, 128
+    with tempfile.TemporaryDirectory() as d:
+        _write_synth_jpegs(d, unique, unique)
+        uniq = [open(os.path.join(d, f"{i:05d}.jpg"), "rb").read() for i in range(unique)]
+    files = [uniq[i % unique] for i in range(n)]
+    t0 = time.perf_counter()
+    descs = [jpeg.parse(f) for f in files]
+    t_parse = time.perf_counter() - t0
+    ms_call = _time_launch(lambda: jpeg.decode_batch(files, descs, device=dev), steps)
+    # kernel-only: rebuild the device buffers once, then replay vip_jpeg_decode
+    arr = (jpeg.JpegDesc * n)()
+    total = 0
+    for i, (f, dsc) in enumerate(zip(files, descs)):
+        C.memmove(C.byref(arr[i]), C.byref(dsc), jpeg.DESC_BYTES)
+        arr[i].file_offset = total
+        total += (len(f) + 15) // 16 * 16
+    db, cb = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.lib().vip_jpeg_plan(arr, n, C.byref(db), C.byref(cb)), "vip_jpeg_plan")
+    host = np.zeros((total,), np.uint8)
+    for i, f in enumerate(files):
+        host[arr[i].file_offset: arr[i].file_offset + len(f)] = np.frombuffer(f, np.uint8)
+    data_d = torch.from_numpy(host).to(dev)
+    desc_d = torch.from_numpy(np.frombuffer(bytes(arr), np.uint8).copy()).to(dev)
+    coef = torch.empty((cb.value * 64,), dtype=torch.int16, device=dev)
+    dst = torch.empty((db.value,), dtype=torch.uint8, device=dev)
+    err = torch.zeros((n,), dtype=torch.int32, device=dev)
+
+    def kern():
+        _lib.check(_lib.lib().vip_jpeg_decode(data_d.data_ptr(), C.addressof(arr), desc_d.data_ptr(), n, coef.data_ptr(),
+                                              dst.data_ptr(), err.data_ptr(), torch.cuda.current_stream().cuda_stream))
+
+    ms_kern = _time_launch(kern, steps)
+    ok = int(err.sum()) == 0 and bool(np.array_equal(dst[: 200 * 200 * 3].cpu().numpy().reshape(200, 200, 3),
+                                                      np.asarray(Image.open(io.BytesIO(files[0])).convert("RGB"))))
+    t0 = time.perf_counter()
+    for f in uniq:
+        np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
+    t_host = (time.perf_counter() - t0) / unique
+    # algorithmic bytes: compressed file in, coefficients out + in (the workspace between the two kernels), pixels out
+    nbytes = total + 2 * cb.value * 128 + db.value
+    return {"workload": f"{n} synthetic 200x200 4:2:0 JPEG files (quality 65..99, mean {total / n / 1024:.1f} KiB) -> u8 RGB",
+            "kernels_ms": ms_kern, "images_per_s_kernels": n / (ms_kern * 1e-3),
+            "decode_batch_ms": ms_call, "images_per_s_from_host_bytes": n / (ms_call * 1e-3),
+            "host_parse_us_per_file": t_parse / n * 1e6,
+            "host_libjpeg_one_core_images_per_s": 1.0 / t_host, "bit_exact_vs_libjpeg_turbo": ok,
+            "roofline": {"bound": "latency (one sequential Huffman stream per warp)", "achieved": nbytes / (ms_kern * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / (ms_kern * 1e-3) / 1e9 / hbm_peak,
+                         "algorithmic_bytes_per_launch": int(nbytes)},
+            "kernel": "jpeg_entropy_kernel + jpeg_pixels_kernel (csrc/jpeg_decode.cu)"}
+
+
 def bench_gcvit_tiny_b256(dev, steps, tc_peak):
     """BASELINE.json configs[2]: GCViT-tiny 224x224 bf16 forward, batch 256, random-init weights, one CUDA graph."""
     import torch
@@ -476,17 +541,26 @@ def bench_main_py(tag, n_images, unique, model_names, tta, rank, world, local_ra
 
     paths = [os.path.join(data, f) for f in pd.read_csv(CFG.test_csv).filename.values[lo:hi]]
     CFG.img_size = (200, 200)
-    ds = build_dataset(paths, labels=None, augment=False, batch_size=128, CFG=CFG)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in ds.host_batches():
-        pass
-    barrier()
-    t_dec = time.perf_counter() - t0
-    t = torch.tensor(times + [t_dec], dtype=torch.float64, device="cuda")
+    t_host = []
+    for mode in ("0", "1"):      # host libjpeg decode (the reference's way) / file read + marker walk (device decode)
+        prev = os.environ.get("VIP_JPEG_DEVICE")
+        os.environ["VIP_JPEG_DEVICE"] = mode
+        ds = build_dataset(paths, labels=None, augment=False, batch_size=128, CFG=CFG)
+        if prev is None:
+            os.environ.pop("VIP_JPEG_DEVICE")
+        else:
+            os.environ["VIP_JPEG_DEVICE"] = prev
+        barrier()
+        t0 = time.perf_counter()
+        for _ in ds.host_batches():
+            pass
+        barrier()
+        t_host.append(time.perf_counter() - t0)
+    t = torch.tensor(times + t_host, dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cold, warm, t_dec = (float(v) for v in t.tolist())
+    cold, warm, t_dec, t_read = (float(v) for v in t.tolist())
+    dev_decode = os.environ.get("VIP_JPEG_DEVICE", "1") != "0"
     os.environ.pop("VIP_DEVICE_BATCH", None)
     res = None
     if rank == 0:
@@ -494,11 +568,14 @@ def bench_main_py(tag, n_images, unique, model_names, tta, rank, world, local_ra
                            f"{world} GPU(s), batch {device_batch or 128}",
                "images": n_images, "wall_s_cold": cold, "wall_s_warm": warm,
                "images_per_s_cold": n_images / cold, "images_per_s_warm": n_images / warm,
-               "host_decode_only_images_per_s": n_images / t_dec, "host_cores": os.cpu_count(),
+               "jpeg_decode": "device (vip_jpeg_decode)" if dev_decode else "host (libjpeg via Pillow)",
+               "host_decode_only_images_per_s": n_images / t_dec, "host_read_parse_only_images_per_s": n_images / t_read,
+               "host_cores": os.cpu_count(),
                "rows_written": int(len(df)), "labels_synthetic_fraction": float(df.logit.mean()),
-               "includes": "file read + libjpeg decode (thread pool), H2D, preprocess + forward graphs, D2H, "
+               "includes": "file read + marker walk (thread pool), H2D of the file bytes, device JPEG decode, preprocess + "
+                           "forward graphs, D2H, "
                            + ("NCCL all_gather, " if world > 1 else "") + "pandas epilogue, CSV write",
-               "limiter": "host JPEG decode" if n_images / t_dec < 1.5 * n_images / warm else "device"}
+               "limiter": "host file read / parse" if (t_read if dev_decode else t_dec) > warm / 1.5 else "device"}
         import shutil
 
         shutil.rmtree(root, ignore_errors=True)
@@ -618,6 +695,7 @@ def run_ours(args):
         if not args.no_extras:
             line["preprocess_nojpeg"] = bench_preprocess_nojpeg(dev, max(5, min(args.steps, 20)), hbm_peak)
             line["gcvit_tiny_b256"] = bench_gcvit_tiny_b256(dev, max(5, min(args.steps, 20)), tc_peak)
+            line["jpeg_decode"] = bench_jpeg_decode(dev, max(5, min(args.steps, 20)), hbm_peak)
         if not args.no_preprocess_only:
             pre_ms = bench_preprocess_only(dev, max(5, min(args.steps, 20)))
             ach = PRE_BYTES_PER_IMAGE * PRE_N / (pre_ms * 1e-3) / 1e9
