@@ -18,6 +18,7 @@ else:
     kw = {}
     if "ln" in ex: kw.update(ln_stats=torch.tensor([0.1, 1.3], device=dev).repeat(m, 1), ln_colsum=torch.randn(n, device=dev))
     if "gelu" in ex: kw.update(act="gelu")
+    if "relu" in ex: kw.update(act="relu")
     if "res" in ex: kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 3, dtype=torch.int64, device=dev))
     if "lo" in ex: kw.update(residual_lo=nn.lo_plane(m, n, dev).zero_(), out_lo=nn.lo_plane(m, n, dev))
     out = torch.empty((m, n), dtype=torch.bfloat16, device=dev)

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvipcup.so")
+LIB_PATH = os.environ.get("VIP_LIB_PATH") or os.path.join(HERE, "libvipcup.so")   # override: A/B experiments only
 
 VIP_DTYPE_F32, VIP_DTYPE_BF16 = 0, 1
 FLAG_HFLIP, FLAG_VFLIP, FLAG_GRAY = 1, 2, 4

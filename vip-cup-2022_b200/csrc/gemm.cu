@@ -778,7 +778,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
         for (int hh = (kShared ? group : 0); hh < (kShared ? group + 1 : 2); ++hh) {
           uint32_t r[32];
+          if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 7 + 3 * (hh & 1)] = clock64();
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + j * 64 + hh * 32), r);
+          if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 8 + 3 * (hh & 1)] = clock64();
           if (j == j_last && hh == (kShared ? group : 1)) release_tmem();
           if (!res_ready) {
             mbar_wait(&rfull_bar[b], (tcount / kSets) & 1);
@@ -806,7 +808,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       // ---- the group's chunks are staged: one fence, one barrier, its stores as one bulk group
+      if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 12] = clock64();
       fence_async_smem();
+      if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 13] = clock64();
       group_sync();
       if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 9] = clock64();
       if (storer && e.out_bf16 != nullptr) {
@@ -1180,9 +1184,11 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
               M, N, K, bn, (int)deep, g.mode, g.conv);
       for (int t = 0; t < 24 && h[t * 16] != 0; ++t) {
         const long long* q = h + t * 16;
-        fprintf(stderr, "  %3d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld | chunk0: ld+%lld math+%lld fence+%lld wait+%lld bar+%lld\n", t,
-                q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[8] - q[5], q[9] - q[8],
-                q[10] - q[9], q[11] - q[10], q[12] - q[11]);
+        // epilogue thread 0: wait before its first TMEM load, the two loads (issue -> data) and the math after each, the
+        // fence, the group barrier, the store issue + statistics tail
+        fprintf(stderr, "  %3d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld | pre %lld ld0 %lld math0 %lld ld1 %lld math1 %lld fence %lld bar %lld tail %lld\n", t,
+                q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - q[5], q[8] - q[7],
+                q[10] - q[8], q[11] - q[10], q[12] - q[11], q[13] - q[12], q[9] - q[13], q[6] - q[9]);
       }
     }
     cudaFree(trace_dev);
