@@ -186,3 +186,38 @@ def test_main_py_bit_reproducible_across_runs_batches_and_gpus(workdir):
     for m in MODELS:
         assert base_p[m].logit.values.tobytes() == multi_p[m].logit.values.tobytes(), f"{m}: 1-GPU vs 2-GPU difference"
     pd.testing.assert_frame_equal(base, multi)
+
+
+@pytest.mark.timeout(900)
+def test_main_py_reads_keras_h5_checkpoints(workdir, tmp_path):
+    """The reference's checkpoint format (ckpts/<base_dir>/ckpt/*.h5, main.py:186-192): the same weights written as Keras
+    HDF5 files -- model.save layout, weight names under the model's name scope -- give byte-identical probabilities to
+    the .npz checkpoints (same softmax heads: k = 2 -> softmax, as main.py:112-114 assumes)."""
+    import json
+    import shutil
+
+    import h5write
+    import make_synth_dataset
+
+    d, models = workdir
+    h5dir = str(tmp_path / "ckpts_h5")
+    entries = json.load(open(os.path.join(models, "ckpts.json")))
+    for name, dim, idx in entries:
+        os.makedirs(os.path.join(h5dir, name, "ckpt"))
+        for f in sorted(os.listdir(os.path.join(models, name, "ckpt"))):
+            z = np.load(os.path.join(models, name, "ckpt", f))
+            assert str(z["__head_act__"]) == "softmax"
+            by_layer = {}
+            for k in z.files:
+                if not k.startswith("__"):
+                    by_layer.setdefault(k.split("/")[0], []).append((f"{name.lower()}/{k}:0", z[k]))
+            h5write.write_keras_weights(os.path.join(h5dir, name, "ckpt", f.replace(".npz", ".h5")), list(by_layer.items()),
+                                        wrap_model_weights=True, leaf_cap=8, node_cap=4)
+    shutil.copy(os.path.join(models, "ckpts.json"), os.path.join(h5dir, "ckpts.json"))
+    data = str(tmp_path / "data")
+    make_synth_dataset.main(data, 40)
+    a_csv, a = run_main(data, models, str(tmp_path / "out_npz" / "pred.csv"))
+    b_csv, b = run_main(data, h5dir, str(tmp_path / "out_h5" / "pred.csv"))
+    assert a_csv.equals(b_csv) and set(a) == set(MODELS)
+    for m in MODELS:
+        assert np.array_equal(a[m].logit.values, b[m].logit.values), m

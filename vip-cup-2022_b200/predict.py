@@ -113,13 +113,14 @@ class GraphedModel:
 
 def _load_model(model_name, model_path, dim, device):
     W, meta = registry.load_checkpoint(model_path)
-    head_key = next((k for k in ("predictions/kernel", "head/kernel", "head/fc/kernel") if k in W), None)
+    head_key = next((k for k in W if k in ("predictions/kernel", "head/kernel", "head/fc/kernel")
+                     or k.endswith(("/predictions/kernel", "/head/kernel", "/head/fc/kernel"))), None)
     if head_key is None:
         raise ValueError(f"{model_path}: no classifier kernel (predictions/kernel, head/kernel, head/fc/kernel) in the checkpoint")
     head_k = W[head_key].shape[1]
     model = registry.create_model(model_name, dim, num_classes=head_k,
                                   head_act=meta["head_act"] or ("sigmoid" if head_k == 1 else "softmax"), device=device)
-    return model.load_weights(W)
+    return model.load_weights(registry.resolve_weight_names(W, list(model.weight_shapes())))
 
 
 def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, index_offset=0):

@@ -2,9 +2,10 @@
 ``base_dir = "<Arch>-<H>x<W>"`` (main.py:43-56, 186-197), mapped onto the B200 model classes.
 
 Checkpoint format: the reference loads full Keras models from ``ckpts/<base_dir>/ckpt/*.h5`` (each file = one fold,
-main.py:187-192).  HDF5 cannot be read offline (no h5py); this build reads ``*.npz`` files holding the same
-Keras-named, Keras-layout weight arrays plus optional ``__num_classes__`` / ``__head_act__`` entries
-(``tests/tools/make_random_ckpts.py`` writes them for the synthetic runs).  ``.h5`` ingestion is listed under "next"."""
+main.py:187-192).  Both formats are read here: Keras HDF5 files through the pure-Python reader ``h5lite`` (no h5py /
+libhdf5 offline; the architecture comes from the directory name, only the weights are taken from the file) and ``*.npz``
+files holding the same Keras-named, Keras-layout weight arrays plus optional ``__num_classes__`` / ``__head_act__`` entries
+(``tests/tools/make_random_ckpts.py`` writes those for the synthetic runs)."""
 from __future__ import annotations
 
 import os
@@ -68,21 +69,52 @@ def scan_checkpoints(model_dir, ckpt_cfg_path):
 
     out = []
     for base_dir, dim, idx in json.load(open(ckpt_cfg_path, "r")):
-        paths = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*.npz")))
-        h5 = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*h5")))
+        paths = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*h5")))        # main.py:187
+        if not paths:
+            paths = sorted(glob(os.path.join(model_dir, base_dir, "ckpt", "*.npz")))
         if paths:
             out.append([paths, dim, idx])
-        elif h5:
-            raise ValueError(f"{base_dir}: Keras .h5 checkpoints cannot be read offline (no HDF5 reader in this build); "
-                             "convert them to .npz with Keras weight names")
         else:
             raise ValueError("no model found for :", base_dir)
     return out
 
 
 def load_checkpoint(path):
+    """One fold -> ({Keras weight name: ndarray}, meta).  ``.h5`` / ``.hdf5``: Keras HDF5 weights (model.save or
+    save_weights), names with the ':0' suffix dropped; ``.npz``: the same dictionary saved with numpy."""
+    if path.endswith((".h5", ".hdf5")):
+        from . import h5lite
+
+        return h5lite.load_keras_weights(path), {"num_classes": None, "head_act": None}
     z = np.load(path, allow_pickle=False)
     W = {k: z[k] for k in z.files if not k.startswith("__")}
     meta = {"num_classes": int(z["__num_classes__"]) if "__num_classes__" in z.files else None,
             "head_act": str(z["__head_act__"]) if "__head_act__" in z.files else None}
     return W, meta
+
+
+def resolve_weight_names(W, expected):
+    """Maps checkpoint names onto the names a model asks for.  Keras prefixes weight names with the name scopes of the
+    enclosing (sub-)models (``<model>/<layer>/kernel``), which depend on how the checkpoint's model object was built; a
+    wanted name is matched exactly or as the unique key that ends with ``/<name>``.  Raises KeyError listing what is
+    missing or ambiguous."""
+    if all(k in W for k in expected):
+        return W
+    if expected:   # one common scope prefix for every weight (the usual case: "<model name>/")
+        for k in W:
+            if k.endswith("/" + expected[0]):
+                prefix = k[: -len(expected[0])]
+                if all(prefix + name in W for name in expected):
+                    return {**W, **{name: W[prefix + name] for name in expected}}
+    out, bad = dict(W), []
+    for name in expected:
+        if name in W:
+            continue
+        hits = [k for k in W if k.endswith("/" + name)]
+        if len(hits) == 1:
+            out[name] = W[hits[0]]
+        else:
+            bad.append(f"{name} ({'missing' if not hits else 'ambiguous: ' + ', '.join(hits[:3])})")
+    if bad:
+        raise KeyError("checkpoint does not provide: " + "; ".join(bad[:8]) + (f" ... (+{len(bad) - 8})" if len(bad) > 8 else ""))
+    return out
