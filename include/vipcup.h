@@ -11,11 +11,11 @@
  *     thread-local human-readable message for the last failure on the calling thread; nothing throws
  *     across the ABI.
  *   - "device" pointers are CUDA device pointers on the current device; "host" pointers are ordinary (ideally
- *     page-locked) host memory.  The caller owns every buffer it passes in; the library owns only what it
- *     creates behind its handles (weights, workspaces).
+ *     page-locked) host memory.  The caller owns every buffer it passes in; the library keeps no state between calls
+ *     (no handles: weights, workspaces and CUDA graphs live in caller-owned device memory, orchestrated from Python).
  *   - all device work is enqueued on the caller's stream (cudaStream_t passed as void*; NULL = legacy default
  *     stream); no hidden synchronisation unless the function name ends in _host / _sync.
- *   - handles are not thread-safe; use one handle per device / rank.
+ *   - calls are thread-compatible: the only library state is the thread-local error text / launch counter.
  *   - there is no CPU fallback: without a CUDA device every compute entry point fails with VIP_ERR_CUDA.
  */
 #ifndef VIPCUP_H_
@@ -183,7 +183,7 @@ int vip_layernorm_bf16(const void* x, const float* gamma, const float* beta, voi
 int vip_dwconv3x3_bf16(const void* x, const float* w, void* out, int64_t* gap, int N, int H, int W, int C, int gelu,
                        void* cuda_stream);
 /* Depthwise K x K convolution, NHWC bf16, explicit zero padding (pad_top / pad_left; the bottom / right padding follows from
- * Ho / Wo), w f32 [K, K, C], bias f32 [C] or NULL, act 0 none / 1 swish / 2 gelu (erf) / 3 relu, gap as for
+ * Ho / Wo), w f32 [K, K, C], bias f32 [C] or NULL, act 0 none / 1 swish / 2 gelu (Keras' erf form evaluated as the fitted tanh of vip_epilogue_t.act) / 3 relu, gap as for
  * vip_dwconv3x3_bf16.  Built: K 3 | 5 with stride 1 | 2, K 7 with stride 1.
  * ConvNeXt: models/tfimm/architectures/convnext.py:192-198 (ZeroPadding2D(3) + DepthwiseConv2D(7) + bias);
  * EfficientNet MBConv: keras_cv_attention_models/efficientnet/efficientnet_v2.py:80-96 (BN folded by the caller). */

@@ -295,8 +295,6 @@ int launch_attention(const bf16* qkv, const bf16* qg, const float* table, bf16* 
 }  // namespace vip
 
 namespace vip {
-int window_attention_tc(const void* qkv, const void* qg, const float* table, void* out, int B, int H, int W, int C, int ws,
-                        int heads, cudaStream_t st);
 int window_attention_ws(const void* qkv, const void* qg, const float* table, void* out, int B, int H, int W, int C, int ws,
                         int heads, cudaStream_t st);
 }
@@ -310,22 +308,18 @@ extern "C" int vip_window_attention_bf16(const void* qkv, const void* q_global, 
               heads);
   VIP_REQUIRE(H % ws == 0 && W % ws == 0, VIP_ERR_INVALID, "vip_window_attention_bf16: H, W must be multiples of ws");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // Three implementations, same results; VIP_ATTN_IMPL = ws (default) | mma | tc.  Measured on B200 (profiles/README.md):
-  // the warp-level mma.sync kernel of this file runs at the legacy-HMMA roofline of sm_100 (~145 TFLOP/s chip-wide); the
-  // one-item-per-CTA tcgen05 kernel (attention_tc.cu) removes the MMA bound but is latency-bound; the persistent
-  // warp-specialised tcgen05 kernel (attention_ws.cu) overlaps the phases of different items.
+  // Two implementations, same results; VIP_ATTN_IMPL = ws (default) | mma.  The persistent warp-specialised tcgen05 kernel
+  // (attention_ws.cu) is the product path; the warp-level mma.sync kernel of this file runs at the legacy-HMMA roofline of
+  // sm_100 (~145 TFLOP/s chip-wide) and serves the shapes whose bias tables do not fit next to the operand ring in shared
+  // memory (ws 14 with more than ~40 heads; tests/test_attention_gpu.py drives that trigger).
   static const int impl = [] {
     const char* v = getenv("VIP_ATTN_IMPL");
-    const char* old = getenv("VIP_ATTN_TCGEN05");
-    if (v != nullptr && v[0] == 'm') return 0;
-    if ((v != nullptr && v[0] == 't') || (old != nullptr && old[0] == '1')) return 1;
-    return 2;
+    return (v != nullptr && v[0] == 'm') ? 0 : 2;
   }();
   if (impl == 2 && (ws == 7 || ws == 14)) {
     const int rc = window_attention_ws(qkv, q_global, rel_table, out, B, H, W, C, ws, heads, st);
     if (rc != VIP_ERR_UNSUPPORTED) return rc;   // else: bias tables too large for shared memory -> mma.sync kernel
   }
-  if (impl == 1 && (ws == 7 || ws == 14)) return window_attention_tc(qkv, q_global, rel_table, out, B, H, W, C, ws, heads, st);
   if (ws == 7)
     return launch_attention<7>((const bf16*)qkv, (const bf16*)q_global, rel_table, (bf16*)out, B, H, W, C, heads, st);
   if (ws == 14)

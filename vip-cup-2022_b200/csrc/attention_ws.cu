@@ -1,6 +1,6 @@
 // Window attention of GCViT (models/gcvit/layers/attention.py:52-83, window.py:3-14 folded into the addressing) as a
 // persistent, warp-specialised tcgen05 kernel -- the default implementation.  attention.cu (warp-level mma.sync) is
-// bound by the legacy HMMA rate of sm_100, attention_tc.cu (one item per CTA, every phase in sequence) by latency; here
+// bound by the legacy HMMA rate of sm_100, a first one-item-per-CTA tcgen05 version (removed) by latency; here
 // one CTA per SM walks a list of items and overlaps the phases of different items:
 //
 //   item      one 128-row query tile group x one PAIR of heads (64 channels = one 128-byte swizzled row):
@@ -652,7 +652,11 @@ int launch_ws(const bf16* qkv, const bf16* qg, const float* table, bf16* out, in
     VIP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int smem = Cfg::smem_bytes(heads);
-  if (smem > smem_max) return VIP_ERR_UNSUPPORTED;   // the caller falls back to the mma.sync kernel
+  if (smem > smem_max) {   // the caller falls back to the mma.sync kernel; the reason stays readable in vip_last_error()
+    set_error("window_attention_ws: %d heads x %d bias entries do not fit in shared memory (%d > %d bytes): mma.sync kernel used",
+              heads, Cfg::TAB, smem, smem_max);
+    return VIP_ERR_UNSUPPORTED;
+  }
   const int ldq = (qg ? 2 : 3) * C;
   CUtensorMap tmQKV, tmQG;
   int rc = make_window_tmap(&tmQKV, qkv, ldq, W, (long long)B * H, WS);

@@ -30,12 +30,6 @@ KEEP_DIMS = [(False, False, False), (False, False), (True,), (True,)]  # gcvit.p
 LN_EPS = 1e-5
 
 
-def _rel_index(ws):  # attention.py:39-50
-    coords = np.stack(np.meshgrid(np.arange(ws), np.arange(ws), indexing="ij")).reshape(2, -1)
-    rel = coords[:, :, None] - coords[:, None, :]
-    return (rel[0] + ws - 1) * (2 * ws - 1) + (rel[1] + ws - 1)
-
-
 FUSED_MLP = os.environ.get("VIP_FUSED_MLP", "1") != "0"   # level-0 MLPs through vip_mlp_fused_bf16
 TWO_PLANE = os.environ.get("VIP_TWO_PLANE", "1") != "0"   # hi + lo bf16 planes for the block residual stream
 
@@ -69,7 +63,7 @@ class GCViT:
 
     # ---- weight packing ------------------------------------------------------------------------------------------
     def _bf(self, a):
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device).to(torch.bfloat16).contiguous()
+        return nn.to_bf16(a, self.device)
 
     def _f32(self, a):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device).contiguous()
@@ -96,10 +90,12 @@ class GCViT:
         k = np.asarray(W[name + "/kernel"], np.float32)
         k = k.reshape(-1, k.shape[-1])                                   # (in, out)
         gamma, beta = np.asarray(W[norm + "/gamma"], np.float32), np.asarray(W[norm + "/beta"], np.float32)
-        wg = torch.from_numpy(np.ascontiguousarray((k * gamma[:, None]).T)).to(torch.bfloat16)   # [out, in], host
-        colsum = wg.float().sum(1).contiguous().to(self.device)          # of the ROUNDED weights: the algebra stays exact
+        wg = self._bf((k * gamma[:, None]).T)                            # [out, in], rounded by vip_cast_f32_bf16
+        # column sums of the ROUNDED weights (the algebra stays exact): bf16 -> f32 is a 16-bit shift, done on the host copy
+        wr = wg.cpu().view(torch.int16).numpy().astype(np.uint16).astype(np.uint32) << 16
+        colsum = self._f32(wr.view(np.float32).sum(1, dtype=np.float32))
         bias = self._f32(beta @ k + np.asarray(W[name + "/bias"], np.float32))
-        return wg.to(self.device).contiguous(), bias, colsum
+        return wg, bias, colsum
 
     def _conv3(self, W, name, bias=False):
         k = np.asarray(W[name + "/kernel"], np.float32)  # (3,3,Cin,Cout)

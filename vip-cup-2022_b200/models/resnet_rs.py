@@ -38,7 +38,7 @@ def _fold_conv_bn(W, conv, bnorm, device):
     kp = (kk + 7) // 8 * 8
     wp = np.zeros((co, kp), np.float32)
     wp[:, :kk] = w2
-    return (torch.from_numpy(wp).to(device).to(torch.bfloat16).contiguous(),
+    return (nn.to_bf16(wp, device),
             torch.from_numpy(b - m * s).to(device).contiguous())
 
 
@@ -60,7 +60,7 @@ def _pair_columns(w, bias, cin, cout):
 def _dense(W, name, device):
     k = np.asarray(W[name + "/kernel"], np.float32)
     k = k.reshape(-1, k.shape[-1])  # (1,1,Cin,Cout) -> (Cin,Cout)
-    return (torch.from_numpy(np.ascontiguousarray(k.T)).to(device).to(torch.bfloat16).contiguous(),
+    return (nn.to_bf16(k.T, device),
             torch.from_numpy(np.asarray(W[name + "/bias"], np.float32)).to(device).contiguous())
 
 
@@ -77,7 +77,7 @@ def _se_reduce_on_conv2(W, n, device):
     k1 = np.asarray(W[n + "se_reduce/kernel"], np.float64)[0, 0]                    # (4f, f)
     wc = w3 @ k1                                                                    # (f, f): mean(y2) -> hidden pre-activation
     bc = b3 @ k1 + np.asarray(W[n + "se_reduce/bias"], np.float64)
-    return (torch.from_numpy(np.ascontiguousarray(wc.T.astype(np.float32))).to(device).to(torch.bfloat16).contiguous(),
+    return (nn.to_bf16(wc.T.astype(np.float32), device),
             torch.from_numpy(bc.astype(np.float32)).to(device).contiguous())
 
 
@@ -144,7 +144,7 @@ class ResNetRS:
         for i in (2, 3):   # 32-channel inputs: pixel-pair form (see _pair_columns); used when the map width is even
             wt, bias = p[f"stem{i}"]
             w2, b2 = _pair_columns(wt.float().cpu().numpy(), bias.cpu().numpy(), 32, wt.shape[0])
-            p[f"stem{i}_pair"] = (torch.from_numpy(w2).to(d).to(torch.bfloat16).contiguous(), torch.from_numpy(b2).to(d).contiguous())
+            p[f"stem{i}_pair"] = (nn.to_bf16(w2, d), torch.from_numpy(b2).to(d).contiguous())
         for gi, (f, reps) in enumerate(BLOCK_ARGS[self.depth]):
             for bi in range(reps):
                 n = f"c{gi + 2}_block_{bi}_"

@@ -384,6 +384,15 @@ def cast_bf16(x_f32):
     return out
 
 
+def to_bf16(a, device):
+    """numpy / host f32 array -> bf16 tensor on ``device``: the rounding runs in vip_cast_f32_bf16 on a CUDA device (weight
+    packing at load time); on the CPU (shape-only model objects of the CPU tests) torch's own cast is the stand-in."""
+    import numpy as np
+
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device).contiguous()
+    return cast_bf16(t) if t.is_cuda else t.to(BF16)
+
+
 MLP_FUSED_SHAPES = {(96, 192), (64, 192)}
 
 
