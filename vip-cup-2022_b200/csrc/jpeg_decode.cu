@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(kPixThreads) jpeg_pixels_kernel(const vip_jpeg
   pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ int s_qt[3][64];                       // transposed like the coefficients: [u * 8 + v]
-  __shared__ int s_scr[kPixWarps * 4 * kTrStride];  // transpose scratch
   const vip_jpeg_desc& d = descs[blockIdx.y];
   if (d.status != VIP_JPEG_OK) return;
   const Geo g = geometry(d);
@@ -355,7 +354,6 @@ __global__ void __launch_bounds__(kPixThreads) jpeg_pixels_kernel(const vip_jpeg
   {
     const int warp = tid >> 5, lane = tid & 31;
     const int b = lane >> 3, r = lane & 7;
-    int* scr = s_scr + warp * (4 * kTrStride);
     const int16_t* cimg = coef + d.coef_offset * 64;
     const int iters = (total + 3) >> 2;
     for (int it = warp; it < iters; it += kPixWarps) {
@@ -376,7 +374,7 @@ __global__ void __launch_bounds__(kPixThreads) jpeg_pixels_kernel(const vip_jpeg
       dd[4] = (int)(short)(raw.z & 0xFFFF) * q1.x; dd[5] = (raw.z >> 16) * q1.y;
       dd[6] = (int)(short)(raw.w & 0xFFFF) * q1.z; dd[7] = (raw.w >> 16) * q1.w;
       idct8<true>(dd);                 // column pass (over v)
-      transpose8(dd, scr, b, r);       // lane r holds row y = r
+      transpose8_shfl(dd, r);          // lane r holds row y = r
       idct8<false>(dd);
       uint2 o;
       o.x = __vimin_s32_relu(dd[0], 255) | (__vimin_s32_relu(dd[1], 255) << 8) | (__vimin_s32_relu(dd[2], 255) << 16) |

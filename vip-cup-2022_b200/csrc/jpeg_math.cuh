@@ -57,6 +57,24 @@ __device__ __forceinline__ void idct8(int (&d)[8]) {
   d[4] = (t13 - t0) >> n;
 }
 
+// 8x8 transpose across the 8 lanes of a block group with warp shuffles: three butterfly stages (lane ^ 4, ^ 2, ^ 1), each
+// exchanging the half of the registers whose index differs from the partner's in that bit -- 12 SHFL + 24 SEL, no shared
+// memory, no barrier.  `r` = lane & 7 (row held on entry, column held on exit).
+__device__ __forceinline__ void transpose8_shfl(int (&d)[8], int r) {
+#pragma unroll
+  for (int m = 4; m >= 1; m >>= 1) {
+    const bool up = (r & m) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i & m) continue;
+      const int send = up ? d[i] : d[i | m];
+      const int recv = __shfl_xor_sync(0xffffffffu, send, m);
+      if (up) d[i] = recv;
+      else d[i | m] = recv;
+    }
+  }
+}
+
 // 8x8 transpose across the 8 lanes of a block group through a per-warp smem scratch.
 __device__ __forceinline__ void transpose8(int (&d)[8], int* scr, int b, int r) {
   int4* wp = reinterpret_cast<int4*>(scr + b * kTrStride + r * 8);

@@ -14,8 +14,8 @@
 //   0  tap tables (4 indices + 4 weights per output row / column), quantisation tables
 //   A  stripes of kStripe output rows: vertical taps -> fp32 stripe in smem -> horizontal taps, /255,
 //      quantise to u8, RGB->YCbCr, 2x2 chroma average -> u8 planes in smem        (no-JPEG images store here)
-//   B  8x8 blocks, 8 lanes per block: FDCT rows -> transpose -> FDCT cols -> quantise/dequantise ->
-//      IDCT cols -> transpose -> IDCT rows -> clamp, in place
+//   B  8x8 blocks, 8 lanes per block: FDCT rows -> transpose (warp shuffles) -> FDCT cols -> quantise/dequantise ->
+//      IDCT cols -> transpose (warp shuffles) -> IDCT rows -> clamp, in place
 //   C  fancy chroma upsampling, YCbCr->RGB, *1/255, flips / gray, vectorised stores
 #include <cuda_bf16.h>
 
@@ -175,7 +175,9 @@ struct FastDiv {
   __device__ __forceinline__ int div(int i) const { return d == 1 ? i : (int)__umulhi((unsigned)i, m); }
 };
 
-template <bool kBf16>
+// kShfl: the two 8x8 transposes of a block's DCT round trip go through warp shuffles (default) instead of the per-warp
+// shared-memory scratch (VIP_PRE_SHFL=0; kept for the A/B measurement in bench.py / profiles).
+template <bool kBf16, bool kShfl>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -418,7 +420,8 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
       d[0] = raw.x & 255; d[1] = (raw.x >> 8) & 255; d[2] = (raw.x >> 16) & 255; d[3] = raw.x >> 24;
       d[4] = raw.y & 255; d[5] = (raw.y >> 8) & 255; d[6] = (raw.y >> 16) & 255; d[7] = raw.y >> 24;
       fdct8<true>(d);                 // row r of the block
-      transpose8(d, scr, b, r);       // lane r now holds column u = r, d[v]
+      if (kShfl) transpose8_shfl(d, r);   // lane r now holds column u = r, d[v]
+      else transpose8(d, scr, b, r);
       fdct8<false>(d);
 #pragma unroll
       for (int v = 0; v < 8; ++v) {
@@ -428,7 +431,8 @@ __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a
         d[v] = c < 0 ? -mag : mag;
       }
       idct8<true>(d);                 // column pass (over v)
-      transpose8(d, scr, b, r);       // lane r holds row y = r
+      if (kShfl) transpose8_shfl(d, r);   // lane r holds row y = r
+      else transpose8(d, scr, b, r);
       idct8<false>(d);
       uint2 o;
       o.x = __vimin_s32_relu(d[0], 255) | (__vimin_s32_relu(d[1], 255) << 8) | (__vimin_s32_relu(d[2], 255) << 16) |
@@ -574,7 +578,9 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
               off);
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  auto kern = dst_dtype == VIP_DTYPE_BF16 ? preprocess_kernel<true> : preprocess_kernel<false>;
+  static const bool shfl = [] { const char* v = getenv("VIP_PRE_SHFL"); return v == nullptr || v[0] != '0'; }();
+  auto kern = dst_dtype == VIP_DTYPE_BF16 ? (shfl ? preprocess_kernel<true, true> : preprocess_kernel<true, false>)
+                                          : (shfl ? preprocess_kernel<false, true> : preprocess_kernel<false, false>);
   VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, off));
   VIP_LAUNCH((kern), N, kThreads, off, st, a);
   VIP_CUDA(cudaGetLastError());
