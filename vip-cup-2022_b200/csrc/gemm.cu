@@ -1106,7 +1106,8 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   // residual the deep configuration is also taken from K > 128 on: its two staging-buffer sets let the producer fetch the
   // next tile's residual a whole tile ahead, which the two-buffer shallow configuration cannot.
   static const int deep_res_kb = [] { const char* v = getenv("VIP_GEMM_DEEP_RES_KB"); return v != nullptr ? atoi(v) : 4; }();
-  const bool deep = g.num_kb > 4 || (epi.residual != nullptr && g.num_kb > deep_res_kb);
+  static const int deep_kb = [] { const char* v = getenv("VIP_GEMM_DEEP_KB"); return v != nullptr ? atoi(v) : 4; }();
+  const bool deep = g.num_kb > deep_kb || (epi.residual != nullptr && g.num_kb > deep_res_kb);
   int bn = pick_bn(M, N, deep, g.conv == 1, g.num_kb);
   // pair mode (two CTAs, tcgen05.mma.cta_group::2, 256-row tiles) for the plain deep GEMMs; VIP_GEMM_PAIR=0 disables
   static const bool pair_env = [] { const char* v = getenv("VIP_GEMM_PAIR"); return v == nullptr || v[0] != '0'; }();

@@ -8,8 +8,9 @@
 // preprocess.cu (jpeg_math.cuh) and is pinned bit for bit against libjpeg-turbo through Pillow (tests/test_jpeg_decode_gpu.py,
 // tests/golden/jpeg_files.npz).  oracle/jpeg_decode.py is the checker, never linked here.
 //
-// Kernel 1 (jpeg_entropy_kernel): one warp per image.  Lanes 0-3 build the four decoding tables of the image in shared
-// memory (10-bit lookahead + the maxcode / valptr arrays of T.81 F.2.2.3 for longer codes); lane 0 then walks the
+// Kernel 1 (jpeg_entropy_kernel): one warp per image.  The warp builds the four decoding tables of the image in shared
+// memory (a 10-bit lookahead table that resolves code + magnitude bits in one lookup when both fit in the window, and the
+// maxcode / valptr arrays of T.81 F.2.2.3 for longer codes); lane 0 then walks the
 // entropy-coded segment (64-bit bit buffer refilled a 32-bit word at a time when the word holds no 0xFF, byte by byte around
 // stuffed zeros, restart markers and the end of the scan) and fills one 8x8 block of coefficients in shared memory; the
 // whole warp writes the block (128 bytes, zeros included) with one coalesced store, so the workspace needs no memset.
@@ -131,39 +132,61 @@ __device__ __forceinline__ void br_refill(BitReader& br) {
   }
 }
 
-__device__ __forceinline__ unsigned br_peek(const BitReader& br, int k) {
-  return (unsigned)(br.acc >> (br.n - k)) & ((1u << k) - 1u);
-}
-
+// Decoding tables of one image.  `fast` is indexed by the next kLook bits of the stream and resolves, in ONE lookup, the
+// Huffman code AND the magnitude bits that follow it whenever both fit in the window (the common case: short codes of
+// small coefficients).  The single thread that walks a stream is bound by the latency of its dependent instruction chain,
+// so the instructions per symbol are what counts:
+//   bit 15 set    complete symbol: bits 0-4 = code length + magnitude bits, 5-8 = zero run, bit 9 = no magnitude (EOB / ZRL
+//                 / DC difference 0), bits 16-31 = the EXTENDed value (T.81 F.2.2.1)
+//   bit 15 clear  nonzero: code of <= kLook bits whose magnitude bits spill over the window: (code length << 8) | symbol
+//                 zero: code longer than kLook bits -> maxcode / valptr search (T.81 F.2.2.3)
 struct HuffTables {
-  unsigned short look[4][1 << kLook];   // (code length << 8) | symbol, 0 = code longer than kLook bits
+  unsigned fast[4][1 << kLook];
   int maxcode[4][17];                   // largest code of each length, -1 if none
   int valoff[4][17];                    // index of the first symbol of that length minus its code
   uint8_t vals[4][256];
 };
 
-// T.81 F.2.2.3 DECODE with a lookahead table in front
-__device__ __forceinline__ int huff_decode(BitReader& br, const HuffTables& T, int t, bool& bad) {
-  const unsigned e = T.look[t][br_peek(br, kLook)];
-  if (e != 0u) {
-    br.n -= (int)(e >> 8);
-    return (int)(e & 255u);
-  }
-#pragma unroll 1
-  for (int l = kLook + 1; l <= 16; ++l) {
-    const int code = (int)br_peek(br, l);
-    if (code <= T.maxcode[t][l]) {
-      br.n -= l;
-      return T.vals[t][(T.valoff[t][l] + code) & 255];
-    }
-  }
-  bad = true;
-  br.n -= 16;
-  return 0;
-}
-
 // T.81 F.2.2.1 EXTEND of the s-bit value v
 __device__ __forceinline__ int huff_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+// One symbol from the 32-bit window w (the next 32 bits of the stream): returns the bits consumed; run / has_val / val out.
+__device__ __forceinline__ int huff_symbol(unsigned w, const HuffTables& T, int t, int& run, bool& has_val, int& val, bool& bad) {
+  const unsigned e = T.fast[t][w >> (32 - kLook)];
+  if (e & 0x8000u) {
+    run = (int)((e >> 5) & 15u);
+    has_val = (e & 0x200u) == 0u;
+    val = (int)e >> 16;
+    return (int)(e & 31u);
+  }
+  int len, rs;
+  if (e != 0u) {
+    len = (int)(e >> 8);
+    rs = (int)(e & 255u);
+  } else {
+    len = 0;
+    rs = 0;
+#pragma unroll 1
+    for (int l = kLook + 1; l <= 16; ++l) {
+      const int code = (int)(w >> (32 - l));
+      if (code <= T.maxcode[t][l]) {
+        len = l;
+        rs = T.vals[t][(T.valoff[t][l] + code) & 255];
+        break;
+      }
+    }
+    if (len == 0) {
+      bad = true;
+      len = 16;
+    }
+  }
+  run = rs >> 4;
+  const int s = rs & 15;
+  has_val = s != 0;
+  val = 0;
+  if (s) val = huff_extend((int)((w << len) >> (32 - s)), s);   // len + s <= 31: inside the window
+  return len + s;
+}
 
 __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restrict__ data, const vip_jpeg_desc* __restrict__ descs,
                                                         int16_t* __restrict__ coef, int32_t* __restrict__ err) {
@@ -180,7 +203,6 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
   }
   const Geo g = geometry(d);
   // ---- tables
-  for (int i = lane; i < 4 * (1 << kLook) / 2; i += 32) reinterpret_cast<unsigned*>(&T.look[0][0])[i] = 0u;
   for (int i = lane; i < 4 * 256 / 4; i += 32)
     reinterpret_cast<unsigned*>(&T.vals[0][0])[i] = reinterpret_cast<const unsigned*>(&d.huff_vals[0][0])[i];
   for (int i = lane; i < 64; i += 32) {
@@ -189,22 +211,39 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
   }
   reinterpret_cast<unsigned*>(blk)[lane] = 0u;
   __syncwarp();
-  if (lane < 4) {
+  if (lane < 4) {   // T.81 Annex C: codes in order of length; maxcode / valptr per length
     const int t = lane;
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
       const int nb = d.huff_bits[t][l - 1];
       T.maxcode[t][l] = nb ? code + nb - 1 : -1;
       T.valoff[t][l] = k - code;
-      for (int i = 0; i < nb; ++i, ++code, ++k) {
-        if (l <= kLook) {
-          const unsigned short e = (unsigned short)((l << 8) | T.vals[t][k & 255]);
-          const int base = code << (kLook - l);
-          for (int j = 0; j < (1 << (kLook - l)); ++j) T.look[t][(base + j) & ((1 << kLook) - 1)] = e;
-        }
-      }
-      code <<= 1;
+      code = (code + nb) << 1;
+      k += nb;
     }
+  }
+  __syncwarp();
+  // fast table: every lane resolves the windows i = lane, lane + 32, ... of the four tables with the canonical search
+  for (int i = lane; i < 4 * (1 << kLook); i += 32) {
+    const int t = i >> kLook;
+    const unsigned win = (unsigned)(i & ((1 << kLook) - 1));
+    unsigned e = 0u;
+    for (int l = 1; l <= kLook; ++l) {
+      const int code = (int)(win >> (kLook - l));
+      if (code <= T.maxcode[t][l]) {
+        const int rs = T.vals[t][(T.valoff[t][l] + code) & 255];
+        const int sz = rs & 15;
+        if (l + sz <= kLook) {
+          int v = 0;
+          if (sz) v = huff_extend((int)((win >> (kLook - l - sz)) & ((1u << sz) - 1u)), sz);
+          e = ((unsigned)(v & 0xFFFF) << 16) | 0x8000u | (sz ? 0u : 0x200u) | ((unsigned)(rs >> 4) << 5) | (unsigned)(l + sz);
+        } else {
+          e = ((unsigned)l << 8) | (unsigned)rs;
+        }
+        break;
+      }
+    }
+    T.fast[t][win] = e;
   }
   __syncwarp();
 
@@ -214,14 +253,15 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
   br.acc = 0;
   br.n = 0;
   br.marker = false;
-  int pred[3] = {0, 0, 0};
+  int pred0 = 0, pred1 = 0, pred2 = 0;
   bool bad = false;
   int until_restart = d.restart_interval;
   int16_t* out = coef + d.coef_offset * 64;
+  const int ncomp = d.ncomp, ri = d.restart_interval;
 
   for (int my = 0; my < g.mcuy; ++my) {
     for (int mx = 0; mx < g.mcux; ++mx) {
-      if (lane == 0 && d.restart_interval > 0) {
+      if (lane == 0 && ri > 0) {
         if (until_restart == 0) {
           // T.81 F.2.2.5 / E.2.4: byte-align, expect RSTm, reset the predictors
           br.n = 0;
@@ -235,44 +275,40 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
           } else {
             bad = true;
           }
-          pred[0] = pred[1] = pred[2] = 0;
-          until_restart = d.restart_interval;
+          pred0 = pred1 = pred2 = 0;
+          until_restart = ri;
         }
         --until_restart;
       }
 #pragma unroll 1
-      for (int c = 0; c < d.ncomp; ++c) {
+      for (int c = 0; c < ncomp; ++c) {
         const int hs = d.hs[c], vs = d.vs[c];
+        const int td = d.td[c], ta = 2 + d.ta[c];
 #pragma unroll 1
         for (int b = 0; b < hs * vs; ++b) {
           const int v = b / hs, h = b - v * hs;
           if (lane == 0 && !bad) {
-            const int td = d.td[c], ta = 2 + d.ta[c];
+            int run, val;
+            bool has_val;
             br_refill(br);
-            int s = huff_decode(br, T, td, bad);
-            int diff = 0;
-            if (s) {
-              s &= 15;
-              diff = huff_extend((int)br_peek(br, s), s);
-              br.n -= s;
-            }
-            pred[c] += diff;
-            blk[0] = (int16_t)pred[c];
+            br.n -= huff_symbol((unsigned)(br.acc >> (br.n - 32)), T, td, run, has_val, val, bad);
+            int pred = c == 0 ? pred0 : (c == 1 ? pred1 : pred2);
+            pred += val;
+            if (c == 0) pred0 = pred;
+            else if (c == 1) pred1 = pred;
+            else pred2 = pred;
+            blk[0] = (int16_t)pred;
             int k = 1;
 #pragma unroll 1
             while (k < 64) {
               br_refill(br);
-              const int rs = huff_decode(br, T, ta, bad);
-              const int r = rs >> 4;
-              s = rs & 15;
-              if (s) {
-                k += r;
-                const int val = huff_extend((int)br_peek(br, s), s);
-                br.n -= s;
+              br.n -= huff_symbol((unsigned)(br.acc >> (br.n - 32)), T, ta, run, has_val, val, bad);
+              if (has_val) {
+                k += run;
                 blk[zzT[k & 63]] = (int16_t)val;
                 if (k > 63) bad = true;
                 ++k;
-              } else if (r == 15) {
+              } else if (run == 15) {
                 k += 16;
               } else {
                 break;

@@ -14,8 +14,8 @@
 //   0  tap tables (4 indices + 4 weights per output row / column), quantisation tables
 //   A  stripes of kStripe output rows: vertical taps -> fp32 stripe in smem -> horizontal taps, /255,
 //      quantise to u8, RGB->YCbCr, 2x2 chroma average -> u8 planes in smem        (no-JPEG images store here)
-//   B  8x8 blocks, 8 lanes per block: FDCT rows -> transpose (warp shuffles) -> FDCT cols -> quantise/dequantise ->
-//      IDCT cols -> transpose (warp shuffles) -> IDCT rows -> clamp, in place
+//   B  8x8 blocks, 8 lanes per block: FDCT rows -> 8-lane transpose -> FDCT cols -> quantise/dequantise ->
+//      IDCT cols -> 8-lane transpose -> IDCT rows -> clamp, in place (transposes: shared-memory scratch or warp shuffles)
 //   C  fancy chroma upsampling, YCbCr->RGB, *1/255, flips / gray, vectorised stores
 #include <cuda_bf16.h>
 
@@ -175,8 +175,8 @@ struct FastDiv {
   __device__ __forceinline__ int div(int i) const { return d == 1 ? i : (int)__umulhi((unsigned)i, m); }
 };
 
-// kShfl: the two 8x8 transposes of a block's DCT round trip go through warp shuffles (default) instead of the per-warp
-// shared-memory scratch (VIP_PRE_SHFL=0; kept for the A/B measurement in bench.py / profiles).
+// kShfl: the two 8x8 transposes of a block's DCT round trip go through warp shuffles (VIP_PRE_SHFL=1) instead of the
+// per-warp shared-memory scratch (default: measured 5 % faster, see vip_preprocess).
 template <bool kBf16, bool kShfl>
 __global__ void __launch_bounds__(kThreads, 2) preprocess_kernel(const PreArgs a) {
   pdl_trigger();
@@ -578,7 +578,10 @@ extern "C" int vip_preprocess(const uint8_t* src, int N, int Hs, int Ws, const i
               off);
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  static const bool shfl = [] { const char* v = getenv("VIP_PRE_SHFL"); return v == nullptr || v[0] != '0'; }();
+  // measured on B200 (benchmarks/pre_shfl_ab.py, 4096 images): shuffle transposes 2.58 ms, shared-memory scratch 2.47 ms --
+  // 12 SHFL + 24 SEL per transpose cost more issue slots than 2 STS.128 + 8 LDS.32 in this issue-bound kernel, so the
+  // scratch stays the default; VIP_PRE_SHFL=1 selects the shuffle version (bit-identical results)
+  static const bool shfl = [] { const char* v = getenv("VIP_PRE_SHFL"); return v != nullptr && v[0] == '1'; }();
   auto kern = dst_dtype == VIP_DTYPE_BF16 ? (shfl ? preprocess_kernel<true, true> : preprocess_kernel<true, false>)
                                           : (shfl ? preprocess_kernel<false, true> : preprocess_kernel<false, false>);
   VIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, off));
