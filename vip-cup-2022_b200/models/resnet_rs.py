@@ -75,8 +75,9 @@ def _se_reduce_on_conv2(W, n, device):
     s = g / np.sqrt(v + BN_EPS)
     w3, b3 = k3 * s[None, :], b - m * s                                             # y3 = y2 @ w3 + b3
     k1 = np.asarray(W[n + "se_reduce/kernel"], np.float64)[0, 0]                    # (4f, f)
+    # float64 products: independent of the host thread count up to ~1e-16, far below the bf16 / f32 roundings that follow
     wc = w3 @ k1                                                                    # (f, f): mean(y2) -> hidden pre-activation
-    bc = b3 @ k1 + np.asarray(W[n + "se_reduce/bias"], np.float64)
+    bc = (b3[:, None] * k1).sum(0) + np.asarray(W[n + "se_reduce/bias"], np.float64)
     return (nn.to_bf16(wc.T.astype(np.float32), device),
             torch.from_numpy(bc.astype(np.float32)).to(device).contiguous())
 
