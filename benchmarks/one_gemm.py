@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One contraction launch for ncu / timing: python benchmarks/one_gemm.py M N K [extras: ln gelu res lo gap<HW>] | conv H C Cout stride
+"""One contraction launch for ncu / timing: python benchmarks/one_gemm.py M N K [extras: ln gelu relu res lo se] | conv H C Cout stride
 (res = residual + row statistics; lo = two-plane residual stream on top of res)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,6 +20,7 @@ else:
     if "gelu" in ex: kw.update(act="gelu")
     if "relu" in ex: kw.update(act="relu")
     if "res" in ex: kw.update(residual=rnd(m, n), row_stats=torch.zeros(m, 3, dtype=torch.int64, device=dev))
+    if "se" in ex: kw.update(residual=rnd(m, n), act="relu", row_gate=torch.rand((m + 168) // 169, n, device=dev), gate_rows=169)
     if "lo" in ex: kw.update(residual_lo=nn.lo_plane(m, n, dev).zero_(), out_lo=nn.lo_plane(m, n, dev))
     out = torch.empty((m, n), dtype=torch.bfloat16, device=dev)
     fn = lambda: nn.gemm(A, w, bias=bias, out=out, **kw)

@@ -317,7 +317,7 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
                                           const float* __restrict__ bias, float& rs_sum, float& rs_sq,
                                           const float* __restrict__ gate_row = nullptr, float pivot = 0.0f,
                                           const __nv_bfloat16* __restrict__ lo_in = nullptr,
-                                          __nv_bfloat16* __restrict__ lo_out = nullptr) {
+                                          __nv_bfloat16* __restrict__ lo_out = nullptr, const uint4* lo_regs = nullptr) {
   constexpr bool kLN = MODE == EPI_LN || MODE == EPI_LN_GELU;
   constexpr bool kGelu = MODE == EPI_GELU || MODE == EPI_LN_GELU;
 #pragma unroll
@@ -363,7 +363,8 @@ __device__ __forceinline__ void epi_row32(const uint32_t (&r)[32], uint8_t* crow
         v[2 * t + 1] += __uint_as_float(w[t] & 0xffff0000u);
       }
       if (lo_in != nullptr) {   // low plane of the two-plane residual stream (null for rows beyond M)
-        const uint4 ul = __ldg(reinterpret_cast<const uint4*>(lo_in + (size_t)(n >> 3) * 256));
+        // lo_regs: fetched before the wait for the tile's MMAs (deep configuration), else one L2 round trip per group here
+        const uint4 ul = lo_regs != nullptr ? lo_regs[q8] : __ldg(reinterpret_cast<const uint4*>(lo_in + (size_t)(n >> 3) * 256));
         const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -707,9 +708,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       //  column block k lies 256 elements further)
       const __nv_bfloat16* lo_in = (e.residual_lo != nullptr && row_ok && !(g.dbg & 64)) ? e.residual_lo + lo_plane_index(row, 0, g.N) : nullptr;
       __nv_bfloat16* lo_out = (e.out_lo != nullptr && row_ok && !(g.dbg & 64)) ? e.out_lo + lo_plane_index(row, 0, g.N) : nullptr;
-      if (lo_in != nullptr) {
-        // the low-plane blocks this thread will read, towards L2 now: the tile's MMAs are still running, and the loads in
-        // the epilogue body would otherwise each expose a DRAM round trip (no registers or shared memory to spare here)
+      // Low-plane values of this thread's 64 columns, fetched NOW (the tile's MMAs are still running): in the body each
+      // group of 8 columns would expose its own L2 / DRAM round trip, four in a row per 32-column piece (timeline: 2.6-4.3 k
+      // cycles of "math" per piece against ~1 k without the planes).  Registers allow it in the one-CTA-per-SM BN = 128
+      // configuration (the level-2 / level-3 proj and fc2 of GCViT); elsewhere the blocks are only pulled towards L2.
+      constexpr bool kLoRegs = kDeep && !kPair && BN == 128;
+      uint4 lo_pre[2][4];
+      bool lo_pre_valid = false;
+      if (kLoRegs && lo_in != nullptr && g.mode == EPI_RES) {
+        lo_pre_valid = true;
+        const int jf = group * kCPG;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int n = n0 + jf * 64 + hh * 32 + q8 * 8;
+            lo_pre[hh][q8] = n < g.N ? __ldg(reinterpret_cast<const uint4*>(lo_in + (size_t)(n >> 3) * 256)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+      } else if (lo_in != nullptr) {
+        // the low-plane blocks this thread will read, towards L2 now (no registers or shared memory to spare here)
         const int jf = kShared ? 0 : group * kCPG;
         for (int j = jf; j < jf + kCPG && n0 + j * 64 < g.N; ++j) {
 #pragma unroll
@@ -722,6 +739,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float pivot = pv_next;
       pv_next = load_pivot(tile + cta_tile_step);
       const float* gate_row = e.row_gate != nullptr ? e.row_gate + (size_t)(min(row, g.M - 1) / e.gate_rows) * g.N : nullptr;
+      {
+        // SE gate of the row's image for this group's chunk: towards L1 while the MMAs run (measured 1-3 % on the conv_3
+        // shapes of ResNet-RS; the same prefetch of the bias / column-sum lines measured +1.5 % on the LN epilogues: dropped)
+        const int c0 = n0 + (kShared ? group * 32 : group * kCPG * 64);
+        if (c0 < g.N) {
+          if (gate_row != nullptr) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(gate_row + c0));
+            if (!kShared) asm volatile("prefetch.global.L1 [%0];" ::"l"(gate_row + min(c0 + 32, g.N - 8)));
+          }
+        }
+      }
       if (kPair) mbar_wait_spin(&tfull_bar[as], aph);
       else mbar_wait(&tfull_bar[as], aph);
       tcgen05_fence_after();
@@ -775,7 +803,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* cbase = cbuf + b * kCBufBytes;
         uint8_t* crow = cbase + rt * 128;
         bool res_ready = !has_res;
-#pragma unroll 1
+#pragma unroll(kLoRegs ? 2 : 1)
         for (int hh = (kShared ? group : 0); hh < (kShared ? group + 1 : 2); ++hh) {
           uint32_t r[32];
           if (g.trace != nullptr && blockIdx.x == 0 && te == 0) g.trace[(tile / cta_tile_step) * 16 + 7 + 3 * (hh & 1)] = clock64();
@@ -796,7 +824,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             case EPI_LN: epi_row32<EPI_LN>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
             case EPI_LN_GELU: epi_row32<EPI_LN_GELU>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq); break;
             case EPI_SE: epi_row32<EPI_SE>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq, gate_row); break;
-            case EPI_RES: epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq, nullptr, pivot, lo_in, lo_out); break;
+            case EPI_RES:
+              epi_row32<EPI_RES>(r, crow, swz, c16, nb, g.N, rstd, nmr, p_colsum, p_bias, ps, pq, nullptr, pivot, lo_in, lo_out,
+                                 (kLoRegs && lo_pre_valid) ? lo_pre[hh & 1] : nullptr);
+              break;
             default:
               epi_generic32(r, crow, swz, c16, nb, g.N, row, g.M, e, has_res, rstd, nmr, p_colsum, p_bias, p_colscale, ps, pq, pivot);
               break;

@@ -94,10 +94,11 @@ class GCViT:
         # column sums of the ROUNDED weights (the algebra stays exact): bf16 -> f32 is a 16-bit shift, done on the host copy
         wr = wg.cpu().view(torch.int16).numpy().astype(np.uint16).astype(np.uint32) << 16
         colsum = self._f32(wr.view(np.float32).sum(1, dtype=np.float32))
-        # beta W in float64 with a fixed summation order: a BLAS matrix-vector product rounds differently with the number
-        # of host threads (torchrun sets OMP_NUM_THREADS=1), which made 1-GPU and 2-GPU runs differ in the last bits
-        bw = (beta.astype(np.float64)[:, None] * k.astype(np.float64)).sum(0)
-        bias = self._f32((bw + np.asarray(W[name + "/bias"], np.float64)).astype(np.float32))
+        # beta W with a fixed summation order (numpy's pairwise f32 sum, like the f32 dot products of the Keras layer): a BLAS
+        # matrix-vector product rounds differently with the number of host threads (torchrun sets OMP_NUM_THREADS=1), which
+        # made 1-GPU and 2-GPU runs differ in the last bits
+        bw = (beta[:, None] * k).sum(0, dtype=np.float32)
+        bias = self._f32(bw + np.asarray(W[name + "/bias"], np.float32))
         return wg, bias, colsum
 
     def _conv3(self, W, name, bias=False):
