@@ -26,7 +26,8 @@ def moments(x, eps=1e-5):
 @pytest.mark.parametrize("m,n,k", [
     (128, 32, 64), (128, 128, 64), (256, 256, 256), (1000, 64, 288), (625 * 3, 512, 1152), (49 * 5, 2048, 512),
     (130, 192 + 64, 96), (4096, 768, 256), (77, 32, 8), (20000, 64, 576),
-    # K > 256 and N >= 128: two-CTA (cta_group::2) tiles of 256 rows, incl. ragged M / N / K tails
+    # K > 256 and N >= 128: deep configuration, incl. ragged M / N / K tails (the same shapes run as two-CTA
+    # cta_group::2 tiles in test_gemm_pair_mode_selected below)
     (5000, 384, 768), (300, 256, 512), (33000, 1152, 384), (257, 128, 320), (1024, 1000, 520),
 ])
 @pytest.mark.parametrize("epi", ["plain", "bias_relu_res", "gelu_f32", "colscale_res"])
@@ -336,3 +337,35 @@ def test_folded_layernorm_with_large_row_mean(cuda_device, c, n):
     torch.cuda.synchronize()
     err = (out.double() - ref).abs().max().item()
     assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_pair_mode_selected(cuda_device):
+    """The two-CTA (tcgen05.mma.cta_group::2, 256-row tiles) configuration only engages for K >= 4096 by default; here the
+    threshold is lowered in a child process (the library reads VIP_GEMM_PAIR_MIN_KB once) so that the deep shapes of the
+    test above -- ragged M / N / K tails included -- run through it, and the kernel name is checked in the trace output."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("VIP_GEMM_PAIR_MIN_KB") == "5":
+        import torch
+
+        from vipcup_b200 import nn
+
+        for m, n, k in [(5000, 384, 768), (300, 256, 512), (33000, 1152, 384), (257, 128, 320), (1024, 1000, 520), (2048, 512, 4096)]:
+            g = torch.Generator(device="cpu").manual_seed(m + n + k)
+            a = (torch.randn(m, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+            b = (torch.randn(n, k, generator=g) * 0.5).to(torch.bfloat16).to(cuda_device)
+            bias = torch.randn(n, generator=g).to(cuda_device)
+            res = torch.randn(m, n, generator=g).to(torch.bfloat16).to(cuda_device)
+            ref = torch.relu(a.float() @ b.float().t() + bias) + res.float()
+            out = nn.gemm(a, b, bias=bias, act="relu", residual=res).float()
+            torch.cuda.synchronize()
+            tol = 2e-2 * max(1.0, ref.abs().max().item())
+            assert (out - ref).abs().max().item() < tol, (m, n, k)
+        return
+    env = dict(os.environ, VIP_GEMM_PAIR_MIN_KB="5", VIP_GEMM_TRACE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-s", __file__, "-k", "pair_mode_selected"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "pair=1" in r.stderr + r.stdout, "the two-CTA configuration was not selected"

@@ -1140,6 +1140,10 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
   static const int deep_kb = [] { const char* v = getenv("VIP_GEMM_DEEP_KB"); return v != nullptr ? atoi(v) : 4; }();
   const bool deep = g.num_kb > deep_kb || (epi.residual != nullptr && g.num_kb > deep_res_kb);
   int bn = pick_bn(M, N, deep, g.conv == 1, g.num_kb);
+  {
+    static const int force_bn = [] { const char* v = getenv("VIP_GEMM_FORCE_BN"); return v != nullptr ? atoi(v) : 0; }();
+    if (force_bn == 64 || force_bn == 128 || (force_bn == 256 && deep)) bn = force_bn;   // tile-width experiments
+  }
   // pair mode (two CTAs, tcgen05.mma.cta_group::2, 256-row tiles) for the plain deep GEMMs; VIP_GEMM_PAIR=0 disables
   static const bool pair_env = [] { const char* v = getenv("VIP_GEMM_PAIR"); return v == nullptr || v[0] != '0'; }();
   // Measured (profiles/README.md): 76 % of the cuBLAS peak at 8192^3 against 71 % for one CTA per tile, but no gain below
@@ -1212,8 +1216,8 @@ int run(const CUtensorMap& tmA, const __nv_bfloat16* B, int ldb, long long M, in
       static long long h[2048 * 16];
       cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
       const long long t0 = h[0];
-      fprintf(stderr, "gemm trace M=%lld N=%d K=%d bn=%d deep=%d mode=%d conv=%d: tile | load-issue begin end | mma tmem-free first-full commit | epi begin end\n",
-              M, N, K, bn, (int)deep, g.mode, g.conv);
+      fprintf(stderr, "gemm trace M=%lld N=%d K=%d bn=%d deep=%d pair=%d mode=%d conv=%d: tile | load-issue begin end | mma tmem-free first-full commit | epi begin end\n",
+              M, N, K, bn, (int)deep, (int)pair, g.mode, g.conv);
       for (int t = 0; t < 24 && h[t * 16] != 0; ++t) {
         const long long* q = h + t * 16;
         // epilogue thread 0: wait before its first TMEM load, the two loads (issue -> data) and the math after each, the
