@@ -9,7 +9,7 @@
 // tests/golden/jpeg_files.npz).  oracle/jpeg_decode.py is the checker, never linked here.
 //
 // Kernel 1 (jpeg_entropy_kernel): one warp per image.  The warp builds the four decoding tables of the image in shared
-// memory (a 10-bit lookahead table that resolves code + magnitude bits in one lookup when both fit in the window, and the
+// memory (an 11-bit lookahead table that resolves code + magnitude bits in one lookup when both fit in the window, and the
 // maxcode / valptr arrays of T.81 F.2.2.3 for longer codes); lane 0 then walks the
 // entropy-coded segment (64-bit bit buffer refilled a 32-bit word at a time when the word holds no 0xFF, byte by byte around
 // stuffed zeros, restart markers and the end of the scan) and fills one 8x8 block of coefficients in shared memory; the
@@ -31,7 +31,8 @@
 namespace vip {
 namespace {
 
-constexpr int kLook = 10;                 // lookahead bits of the fast Huffman path
+constexpr int kLook = 11;                 // lookahead bits of the AC tables' fast path (2 x 2048 x 4 B per image)
+constexpr int kLookDC = 9;                // ... of the DC tables (one symbol in 64 is a DC difference)
 constexpr int kPixThreads = 256;
 constexpr int kPixWarps = kPixThreads / 32;
 constexpr int kPlaneBudget = 96 * 1024;   // bytes of component planes per CTA (2 CTAs per SM)
@@ -84,26 +85,34 @@ __host__ __device__ inline int band_rows(const Geo& g) {
 }
 
 // ---- kernel 1: entropy decode -----------------------------------------------------------------------------------------
+// Bit reader of the one thread that walks a stream.  The next bits of the stream sit at the TOP of a 64-bit register (n of
+// them valid, zeros below), so the 32-bit decoding window is simply its high word; consuming k bits is one 64-bit shift.
+// Positions are 32-bit offsets from the start of the entropy-coded segment (short dependent chains: the thread is bound by
+// instruction latency, not by throughput).
 struct BitReader {
-  const uint8_t* p;
-  const uint8_t* end;
-  unsigned long long acc;   // the low n bits are the next bits of the stream, most significant first
-  int n;
+  const uint8_t* base;      // first byte of the entropy-coded segment
+  unsigned pos, end;        // next byte, segment length
+  unsigned mis;             // (address of base) & 3: word loads need pos + mis to be a multiple of 4
+  unsigned long long acc;   // MSB-aligned bit buffer
+  int n;                    // valid bits in acc
   bool marker;              // a marker (or the end of the data) stops the stream: zeros are fed from there on
+  bool have_next;           // next_w holds the (aligned) word at pos, requested one refill earlier: the load latency of
+  unsigned next_w;          // the stream is off the dependent chain (L1 is small next to the tables of ~10 images)
 };
 
 __device__ __forceinline__ void br_byte(BitReader& br) {
   unsigned b = 0;
+  br.have_next = false;
   if (!br.marker) {
-    if (br.p < br.end) {
-      b = __ldg(br.p++);
+    if (br.pos < br.end) {
+      b = __ldg(br.base + br.pos++);
       if (b == 0xFFu) {
-        const unsigned b2 = br.p < br.end ? __ldg(br.p) : 0xD9u;
+        const unsigned b2 = br.pos < br.end ? __ldg(br.base + br.pos) : 0xD9u;
         if (b2 == 0u) {
-          ++br.p;                 // stuffed zero (T.81 B.1.1.5)
+          ++br.pos;               // stuffed zero (T.81 B.1.1.5)
         } else {
-          br.marker = true;       // leave p on the 0xFF of the marker
-          --br.p;
+          br.marker = true;       // leave pos on the 0xFF of the marker
+          --br.pos;
           b = 0;
         }
       }
@@ -111,28 +120,34 @@ __device__ __forceinline__ void br_byte(BitReader& br) {
       br.marker = true;
     }
   }
-  br.acc = (br.acc << 8) | b;
+  br.acc |= (unsigned long long)b << (56 - br.n);
   br.n += 8;
 }
 
-// at least 32 valid bits afterwards
+// more than 32 valid bits afterwards
 __device__ __forceinline__ void br_refill(BitReader& br) {
   while (br.n <= 32) {
-    if (!br.marker && (reinterpret_cast<uintptr_t>(br.p) & 3) == 0 && br.p + 4 <= br.end) {
-      const unsigned w = __ldg(reinterpret_cast<const unsigned*>(br.p));
-      const unsigned inv = ~w;
-      if ((((inv - 0x01010101u) & w) & 0x80808080u) == 0u) {   // no byte of w is 0xFF
-        br.acc = (br.acc << 32) | __byte_perm(w, 0u, 0x0123);
+    if (!br.marker && ((br.pos + br.mis) & 3u) == 0u && br.pos + 4u <= br.end) {
+      const unsigned w = br.have_next ? br.next_w : __ldg(reinterpret_cast<const unsigned*>(br.base + br.pos));
+      if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0u) {   // no byte of w is 0xFF
+        br.acc |= (unsigned long long)__byte_perm(w, 0u, 0x0123) << (32 - br.n);
         br.n += 32;
-        br.p += 4;
+        br.pos += 4u;
+        br.have_next = br.pos + 4u <= br.end;
+        if (br.have_next) br.next_w = __ldg(reinterpret_cast<const unsigned*>(br.base + br.pos));   // used ~3 symbols later
         continue;
       }
     }
     br_byte(br);
   }
 }
+__device__ __forceinline__ unsigned br_window(const BitReader& br) { return (unsigned)(br.acc >> 32); }
+__device__ __forceinline__ void br_consume(BitReader& br, int k) {
+  br.acc <<= k;
+  br.n -= k;
+}
 
-// Decoding tables of one image.  `fast` is indexed by the next kLook bits of the stream and resolves, in ONE lookup, the
+// Decoding tables of one image.  `fast_*` is indexed by the next kLook (AC) / kLookDC bits of the stream and resolves, in ONE lookup, the
 // Huffman code AND the magnitude bits that follow it whenever both fit in the window (the common case: short codes of
 // small coefficients).  The single thread that walks a stream is bound by the latency of its dependent instruction chain,
 // so the instructions per symbol are what counts:
@@ -141,7 +156,8 @@ __device__ __forceinline__ void br_refill(BitReader& br) {
 //   bit 15 clear  nonzero: code of <= kLook bits whose magnitude bits spill over the window: (code length << 8) | symbol
 //                 zero: code longer than kLook bits -> maxcode / valptr search (T.81 F.2.2.3)
 struct HuffTables {
-  unsigned fast[4][1 << kLook];
+  unsigned fast_dc[2][1 << kLookDC];
+  unsigned fast_ac[2][1 << kLook];
   int maxcode[4][17];                   // largest code of each length, -1 if none
   int valoff[4][17];                    // index of the first symbol of that length minus its code
   uint8_t vals[4][256];
@@ -151,8 +167,10 @@ struct HuffTables {
 __device__ __forceinline__ int huff_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
 
 // One symbol from the 32-bit window w (the next 32 bits of the stream): returns the bits consumed; run / has_val / val out.
+// t = table index into maxcode / valoff / vals (0, 1 DC; 2, 3 AC); kBits = lookahead of that table's fast path.
+template <int kBits>
 __device__ __forceinline__ int huff_symbol(unsigned w, const HuffTables& T, int t, int& run, bool& has_val, int& val, bool& bad) {
-  const unsigned e = T.fast[t][w >> (32 - kLook)];
+  const unsigned e = kBits == kLookDC ? T.fast_dc[t & 1][w >> (32 - kBits)] : T.fast_ac[t & 1][w >> (32 - kBits)];
   if (e & 0x8000u) {
     run = (int)((e >> 5) & 15u);
     has_val = (e & 0x200u) == 0u;
@@ -167,7 +185,7 @@ __device__ __forceinline__ int huff_symbol(unsigned w, const HuffTables& T, int 
     len = 0;
     rs = 0;
 #pragma unroll 1
-    for (int l = kLook + 1; l <= 16; ++l) {
+    for (int l = kBits + 1; l <= 16; ++l) {
       const int code = (int)(w >> (32 - l));
       if (code <= T.maxcode[t][l]) {
         len = l;
@@ -223,19 +241,22 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
     }
   }
   __syncwarp();
-  // fast table: every lane resolves the windows i = lane, lane + 32, ... of the four tables with the canonical search
-  for (int i = lane; i < 4 * (1 << kLook); i += 32) {
-    const int t = i >> kLook;
-    const unsigned win = (unsigned)(i & ((1 << kLook) - 1));
+  // fast tables: every lane resolves the windows i = lane, lane + 32, ... of the four tables with the canonical search
+  for (int i = lane; i < 2 * (1 << kLookDC) + 2 * (1 << kLook); i += 32) {
+    const bool dc = i < 2 * (1 << kLookDC);
+    const int bits = dc ? kLookDC : kLook;
+    const int j = dc ? i : i - 2 * (1 << kLookDC);
+    const int t = (dc ? 0 : 2) + (j >> bits);
+    const unsigned win = (unsigned)(j & ((1 << bits) - 1));
     unsigned e = 0u;
-    for (int l = 1; l <= kLook; ++l) {
-      const int code = (int)(win >> (kLook - l));
+    for (int l = 1; l <= bits; ++l) {
+      const int code = (int)(win >> (bits - l));
       if (code <= T.maxcode[t][l]) {
         const int rs = T.vals[t][(T.valoff[t][l] + code) & 255];
         const int sz = rs & 15;
-        if (l + sz <= kLook) {
+        if (l + sz <= bits) {
           int v = 0;
-          if (sz) v = huff_extend((int)((win >> (kLook - l - sz)) & ((1u << sz) - 1u)), sz);
+          if (sz) v = huff_extend((int)((win >> (bits - l - sz)) & ((1u << sz) - 1u)), sz);
           e = ((unsigned)(v & 0xFFFF) << 16) | 0x8000u | (sz ? 0u : 0x200u) | ((unsigned)(rs >> 4) << 5) | (unsigned)(l + sz);
         } else {
           e = ((unsigned)l << 8) | (unsigned)rs;
@@ -243,16 +264,21 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
         break;
       }
     }
-    T.fast[t][win] = e;
+    if (dc) T.fast_dc[t & 1][win] = e;
+    else T.fast_ac[t & 1][win] = e;
   }
   __syncwarp();
 
   BitReader br;
-  br.p = data + d.file_offset + d.scan_offset;
-  br.end = br.p + d.scan_bytes;
+  br.base = data + d.file_offset + d.scan_offset;
+  br.pos = 0u;
+  br.end = (unsigned)d.scan_bytes;
+  br.mis = (unsigned)(reinterpret_cast<uintptr_t>(br.base) & 3u);
   br.acc = 0;
   br.n = 0;
   br.marker = false;
+  br.have_next = false;
+  br.next_w = 0u;
   int pred0 = 0, pred1 = 0, pred2 = 0;
   bool bad = false;
   int until_restart = d.restart_interval;
@@ -269,8 +295,8 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
           if (!br.marker) br_byte(br);             // must run into the marker at once
           br.n = 0;
           br.acc = 0;
-          if (br.marker && br.p + 2 <= br.end && br.p[0] == 0xFF && (br.p[1] & 0xF8) == 0xD0) {
-            br.p += 2;
+          if (br.marker && br.pos + 2u <= br.end && br.base[br.pos] == 0xFF && (br.base[br.pos + 1] & 0xF8) == 0xD0) {
+            br.pos += 2u;
             br.marker = false;
           } else {
             bad = true;
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
             int run, val;
             bool has_val;
             br_refill(br);
-            br.n -= huff_symbol((unsigned)(br.acc >> (br.n - 32)), T, td, run, has_val, val, bad);
+            br_consume(br, huff_symbol<kLookDC>(br_window(br), T, td, run, has_val, val, bad));
             int pred = c == 0 ? pred0 : (c == 1 ? pred1 : pred2);
             pred += val;
             if (c == 0) pred0 = pred;
@@ -302,7 +328,7 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
 #pragma unroll 1
             while (k < 64) {
               br_refill(br);
-              br.n -= huff_symbol((unsigned)(br.acc >> (br.n - 32)), T, ta, run, has_val, val, bad);
+              br_consume(br, huff_symbol<kLook>(br_window(br), T, ta, run, has_val, val, bad));
               if (has_val) {
                 k += run;
                 blk[zzT[k & 63]] = (int16_t)val;
