@@ -12,8 +12,11 @@ one batch; the whole step is one CUDA graph.
   e2e           same path through EnsemblePredictor.predict_host_many: every step copies its batch from pinned host
                 memory (copy stream, overlapping the previous step's graph) and its [B] probabilities back, all inside the
                 timed region
-  roofline      tensor-bound: algorithmic FLOPs of the step (31.06 GFLOP/image) / CUDA-event step time /
-                measured sustained bf16 peak; the tcgen05 GEMM / implicit-conv kernel is the dominant kernel
+  roofline      the dominant kernel (tcgen05 GEMM / implicit-conv: 75 % of the step) timed alone with CUDA events on its
+                heaviest shape (GCViT-small level-2 qkv), 2MNK / launch time against the measured sustained bf16 peak;
+                traffic = DRAM bytes of one launch from the committed ncu capture
+  roofline_step the whole step: algorithmic FLOPs (31.06 GFLOP/image) / CUDA-event step time / the same peak
+  jpeg_decode   device JPEG decode of 1024 files: kernels alone and from host bytes, host libjpeg beside it
   preprocess_only  BASELINE.json configs[1] (augment pipeline on a 4096-image batch, HBM-bound declaration) with its own
                 roofline object -- the kernel `roofline.traffic` was captured for
   preprocess_nojpeg  the preprocessing main.py actually runs (no crop, no JPEG emulation): the streaming kernel at
@@ -53,19 +56,24 @@ PRE_N, PRE_HO = 4096, 224
 PRE_BYTES_PER_IMAGE = HS * WS * 3 + PRE_HO * PRE_HO * 3 * 4  # 722 112 algorithmic bytes
 
 
+_TC_BURST = 1651.5   # cuBLAS bf16 burst figure: the denominator for a kernel timed alone (the sustained one for a long step)
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
+        global _TC_BURST
+        _TC_BURST = float(p.get("bf16_tflops", p["bf16_tflops_sustained"]))
         return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic():
+def _traffic(key="preprocess_kernel_dram_bytes_per_launch"):
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get("preprocess_kernel_dram_bytes_per_launch")
+            return json.load(f).get(key)
     except Exception:
         return None
 
@@ -398,6 +406,33 @@ def bench_jpeg_decode(dev, steps, hbm_peak):
             "kernel": "jpeg_entropy_kernel + jpeg_pixels_kernel (csrc/jpeg_decode.cu)"}
 
 
+def bench_dominant_kernel(dev, steps):
+    """The dominant kernel of the step on its heaviest shape, timed alone with CUDA events: gemm_tcgen05_kernel<256,1,0> on
+    the GCViT-small level-2 qkv contraction (M = 1024 x 196 tokens, N = 1152, K = 384, LayerNorm folded into the epilogue;
+    19 launches per step -- the contraction kernels are 75 % of the step, profiles/r2_bench_configs3_launches_final.txt).
+    Three operand / output sets (1.85 GB) are cycled so that no launch finds its operands in the 126 MB L2."""
+    import torch
+
+    from vipcup_b200 import nn
+
+    m, n, k, sets = 1024 * 196, 1152, 384, 3
+    a = [(torch.randn(m, k, device=dev) * 0.5).to(torch.bfloat16) for _ in range(sets)]
+    w = (torch.randn(n, k, device=dev) * 0.05).to(torch.bfloat16)
+    out = [torch.empty((m, n), dtype=torch.bfloat16, device=dev) for _ in range(sets)]
+    bias, colsum = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    stats = torch.tensor([0.1, 1.3], device=dev).repeat(m, 1).contiguous()
+    i = [0]
+
+    def fn():
+        j = i[0] % sets
+        i[0] += 1
+        nn.gemm(a[j], w, bias=bias, out=out[j], ln_stats=stats, ln_colsum=colsum)
+
+    ms = _time_launch(fn, max(steps, 9))
+    return {"kernel": "gemm_tcgen05_kernel<256,1,0> (GCViT-small level-2 qkv: M 200704, N 1152, K 384, folded LayerNorm)",
+            "ms_per_launch": ms, "flops_per_launch": 2.0 * m * n * k, "tflops": 2.0 * m * n * k / (ms * 1e-3) / 1e12}
+
+
 def bench_gcvit_tiny_b256(dev, steps, tc_peak):
     """BASELINE.json configs[2]: GCViT-tiny 224x224 bf16 forward, batch 256, random-init weights, one CUDA graph."""
     import torch
@@ -668,6 +703,7 @@ def run_ours(args):
         hbm_peak, tc_peak, peak_src = _peaks()
         step_ms = total_ms / args.steps
         achieved_tf = GFLOP_PER_IMAGE * BATCH / step_ms  # GFLOP / ms = TFLOP/s
+        dom = bench_dominant_kernel(dev, 9)
         line = {
             "metric": METRIC, "value": world * BATCH * args.steps / (total_ms * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": step_ms,
@@ -684,13 +720,19 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(src_h.nbytes), "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps,
                     "api": "EnsemblePredictor.predict_host_many (per step: pinned host u8 batch -> H2D on a copy stream, overlapping the previous step -> CUDA graph -> D2H [B] f64)"},
             "gpu_launches": int(pred.launches_per_step or 0) * args.steps * world,
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tc_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / tc_peak, "traffic": None,
-                         "kernel": "gemm_tcgen05_kernel (tcgen05 GEMM / implicit-GEMM conv), whole-step average",
-                         "peak_source": peak_src + ", sustained bf16 figure (kernel timed inside a long step)",
-                         "algorithmic_flops_per_step": GFLOP_PER_IMAGE * 1e9 * BATCH,
-                         "note": "achieved = algorithmic FLOPs of the step / CUDA-event step time (all kernels of the step, "
-                                 "not only the GEMMs); per-kernel shares: profiles/"},
+            "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": _TC_BURST, "unit": "TFLOP/s",
+                         "frac": dom["tflops"] / _TC_BURST, "frac_of_sustained_peak": dom["tflops"] / tc_peak,
+                         "traffic": _traffic("gemm_L2qkv_dram_bytes_per_launch"),
+                         "kernel": dom["kernel"], "ms_per_launch": dom["ms_per_launch"],
+                         "algorithmic_flops_per_launch": dom["flops_per_launch"],
+                         "peak_source": peak_src + ", burst bf16 figure (kernel timed alone)",
+                         "note": "dominant kernel timed alone with CUDA events on its heaviest shape (19 launches per step), "
+                                 "operands cycled through 1.85 GB so that none is L2-resident; traffic = dram bytes read + "
+                                 "written of one launch from profiles/r2_gemm_L2qkv_ncu_full.txt"},
+            "roofline_step": {"bound": "tensor", "achieved": achieved_tf, "peak": tc_peak, "unit": "TFLOP/s",
+                              "frac": achieved_tf / tc_peak, "algorithmic_flops_per_step": GFLOP_PER_IMAGE * 1e9 * BATCH,
+                              "note": "algorithmic FLOPs of the whole step / CUDA-event step time (every kernel of the step: "
+                                      "contractions 75 %, window attention 10 %, HBM-bound layer kernels 15 %)"},
         }
         if not args.no_extras:
             line["preprocess_nojpeg"] = bench_preprocess_nojpeg(dev, max(5, min(args.steps, 20)), hbm_peak)
