@@ -156,10 +156,18 @@ def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, inde
                        batch_size=chunk, drop_remainder=False, CFG=CFG, device=dev, index_offset=index_offset)
     shared, outs = {}, []
     use_graph = os.environ.get("VIP_GRAPH", "1") != "0"
+    prof = os.environ.get("VIP_PROFILE", "0") == "1"     # wall-clock breakdown of the host loop on stderr
+    import time as _time
+    tm = {"wait_files": 0.0, "stage": 0.0, "enqueue": 0.0, "drain": 0.0}
     for pass_idx in range(tta):
+        t_prev = _time.perf_counter()
         for i0, imgs in ds.host_batches():
+            t0 = _time.perf_counter()
+            tm["wait_files"] += t0 - t_prev
             flags_h = ds.flags_for(i0, len(imgs), pass_idx) if tta > 1 else None
             src = ds.stage(imgs)
+            tm["stage"] += _time.perf_counter() - t0
+            t0 = _time.perf_counter()
             flags = None if flags_h is None else torch.from_numpy(np.ascontiguousarray(flags_h)).to(dev, non_blocking=True)
             for e in entries:
                 if "runner" not in e:           # first batch: weights to the device, graph capture at this source size
@@ -194,8 +202,16 @@ def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, inde
                     e["pos"] = 0
                 e["out"][e["pos"]: e["pos"] + pr.shape[0]] = pr
                 e["pos"] += pr.shape[0]
+            t_prev = _time.perf_counter()
+            tm["enqueue"] += t_prev - t0
+    t0 = _time.perf_counter()
     for e in entries:
         outs.append(e["out"].cpu().numpy())
+    tm["drain"] = _time.perf_counter() - t0
+    if prof:
+        import sys as _sys
+
+        print("predict_device wall split (s): " + ", ".join(f"{k} {v:.3f}" for k, v in tm.items()), file=_sys.stderr)
     return outs, fold_counts
 
 
@@ -230,7 +246,14 @@ def predict_soln(CFG, ensemble=False, strategy=None, predict_fn=None, runner_cac
                 raw.append(predict_fn(model_name, model_path, dim, local_paths))
             fold_counts.append(len(model_paths))
     else:
+        import time as _time
+
+        _t0 = _time.perf_counter()
         raw, fold_counts = predict_device(CFG, local_paths, tta, verbose, runner_cache, index_offset=lo)
+        if os.environ.get("VIP_PROFILE", "0") == "1":
+            import sys as _sys
+
+            print(f"predict_soln: setup + predict_device {_time.perf_counter() - _t0:.3f} s", file=_sys.stderr)
     local_rows = [aggregate_model(np.asarray(pred, np.float32), tta, n_local, CFG.agg)[:, 0] for pred in raw]
 
     # one exchange step: [sum(folds), n_local] float32 per rank -> [sum(folds), N] everywhere
