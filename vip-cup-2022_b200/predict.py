@@ -99,6 +99,17 @@ class GraphedModel:
     def __call__(self, src, flags):
         """src uint8 [b,Hs,Ws,3] on the device, flags uint8 [b] or None -> float32 [b,k] (valid until the next call)."""
         sh = self.shared
+        n = src.shape[0]
+        if (self.graph is not None and n < sh.batch and 4 * n >= sh.batch and tuple(src.shape[1:]) == tuple(sh.src.shape[1:])):
+            # a tail that is at least a quarter of the graph's batch: run the graph on a padded batch (the unused slots keep
+            # the previous batch's images; per-image results do not depend on their neighbours) and keep the first n rows
+            sh.src[:n].copy_(src, non_blocking=True)
+            if flags is None:
+                sh.flags.zero_()
+            else:
+                sh.flags[:n].copy_(flags, non_blocking=True)
+            self.graph.replay()
+            return self.probs[:n].clone()
         if self.graph is not None and tuple(src.shape) == tuple(sh.src.shape):
             if src.data_ptr() != sh.src.data_ptr():
                 sh.src.copy_(src, non_blocking=True)
@@ -150,6 +161,13 @@ def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, inde
         fold_counts.append(len(model_paths))
     if n_local == 0:
         return [np.zeros((0, 1), np.float32) for _ in entries], fold_counts
+    if len({e["bs"] for e in entries}) == 1:
+        # equal batches instead of full ones plus a ragged tail (results do not depend on the batch an image is in): the
+        # tail would run eagerly, ~450 library calls per model instead of one graph replay
+        bs = entries[0]["bs"]
+        bs = -(-n_local // -(-n_local // bs))
+        for e in entries:
+            e["bs"] = bs
     chunk = max(e["bs"] for e in entries)
     CFG.batch_size, CFG.img_size = chunk, entries[0]["dim"]
     ds = build_dataset(local_paths, labels=None, augment=tta > 1, repeat=True, cache=False, shuffle=False,
