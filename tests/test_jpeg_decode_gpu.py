@@ -100,6 +100,9 @@ def test_corrupt_stream_is_flagged_not_fatal(cuda_device):
     assert np.array_equal(batch.image(0).cpu().numpy(), _pillow(good)) and np.array_equal(batch.image(2).cpu().numpy(), _pillow(good))
     got = batch.image(1).cpu().numpy()                                      # the rows decoded before the cut are right
     assert np.array_equal(got[:32], _pillow(good)[:32])
+    assert batch.err.cpu().tolist() == [0, 1, 0]                            # bits consumed past the end of the scan
+    with pytest.raises(_lib.VipError):
+        batch.check()
     assert jpeg.decode_batch([], device=cuda_device).flat.numel() == 1      # empty batch
 
 
@@ -129,3 +132,29 @@ def test_photos_decode_and_dataset_path(cuda_device, tmp_path):
             os.environ.pop("VIP_JPEG_DEVICE", None)
     assert outs["1"].shape == (6, 224, 224, 3)
     assert np.array_equal(outs["1"].view(np.uint32), outs["0"].view(np.uint32))
+
+
+def test_dataset_raises_for_corrupt_file(cuda_device, tmp_path):
+    """A truncated entropy-coded segment: the device decoder flags it and the dataset raises after the pass, as
+    tf.image.decode_jpeg would for the file."""
+    import torch
+
+    from oracle import preprocess as P
+    from vipcup_b200.config import Config
+    from vipcup_b200.dataset import build_dataset
+    from vipcup_b200 import jpeg
+
+    good = _enc(P.synth_image(2), quality=80)
+    d = jpeg.parse(good)
+    paths = []
+    for i, data in enumerate([good, good[: d.scan_offset + d.scan_bytes // 2] + b"\xff\xd9", good]):
+        p = str(tmp_path / f"f{i}.jpg")
+        with open(p, "wb") as f:
+            f.write(data)
+        paths.append(p)
+    ds = build_dataset(paths, batch_size=8, CFG=Config({"img_size": [200, 200], "seed": 1}), augment=False, device=cuda_device)
+    for _ in ds:
+        pass
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="f1.jpg"):
+        ds.check_decode_errors()

@@ -96,6 +96,7 @@ struct BitReader {
   unsigned long long acc;   // MSB-aligned bit buffer
   int n;                    // valid bits in acc
   bool marker;              // a marker (or the end of the data) stops the stream: zeros are fed from there on
+  int fake;                 // zero bits fed past a marker / the end of the data and still inside acc or already consumed
   bool have_next;           // next_w holds the (aligned) word at pos, requested one refill earlier: the load latency of
   unsigned next_w;          // the stream is off the dependent chain (L1 is small next to the tables of ~10 images)
 };
@@ -120,6 +121,7 @@ __device__ __forceinline__ void br_byte(BitReader& br) {
       br.marker = true;
     }
   }
+  if (br.marker) br.fake += 8;
   br.acc |= (unsigned long long)b << (56 - br.n);
   br.n += 8;
 }
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
   br.marker = false;
   br.have_next = false;
   br.next_w = 0u;
+  br.fake = 0;
   int pred0 = 0, pred1 = 0, pred2 = 0;
   bool bad = false;
   int until_restart = d.restart_interval;
@@ -290,6 +293,8 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
       if (lane == 0 && ri > 0) {
         if (until_restart == 0) {
           // T.81 F.2.2.5 / E.2.4: byte-align, expect RSTm, reset the predictors
+          if (br.fake > br.n) bad = true;          // the interval consumed bits that were never in the file
+          br.fake = 0;
           br.n = 0;
           br.acc = 0;
           if (!br.marker) br_byte(br);             // must run into the marker at once
@@ -298,6 +303,7 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
           if (br.marker && br.pos + 2u <= br.end && br.base[br.pos] == 0xFF && (br.base[br.pos + 1] & 0xF8) == 0xD0) {
             br.pos += 2u;
             br.marker = false;
+            br.fake = 0;
           } else {
             bad = true;
           }
@@ -350,7 +356,9 @@ __global__ void __launch_bounds__(32) jpeg_entropy_kernel(const uint8_t* __restr
       }
     }
   }
-  if (err != nullptr && lane == 0) err[blockIdx.x] = bad ? 1 : 0;
+  // zero bits fed after the marker that ends the scan are legitimate read-ahead only while they stay unconsumed (libjpeg
+  // warns "premature end of data segment" and pads; tf.image.decode_jpeg rejects such a file)
+  if (err != nullptr && lane == 0) err[blockIdx.x] = (bad || br.fake > br.n) ? 1 : 0;
 }
 
 // ---- kernel 2: dequantise, IDCT, upsample, colour ------------------------------------------------------------------------

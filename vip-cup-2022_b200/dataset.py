@@ -106,6 +106,8 @@ class RawJpegs(list):
     def decoded(self, device):
         if getattr(self, "_decoded", None) is None:
             self._decoded = jpeg.decode_batch([f for f, _ in self], [d for _, d in self], device=device)
+            if self._decoded.err is not None and getattr(self, "err_sink", None) is not None:
+                self.err_sink.append((getattr(self, "first_index", 0), self._decoded.err))   # read after the pass: no sync here
         return self._decoded
 
 
@@ -121,6 +123,7 @@ class DeviceDataset:
         self.out_dtype, self.device = out_dtype, device
         # JPEG decode on the device unless the caller brought a decoder of its own or switched it off
         self.device_decode = (getattr(decode_fn, "device_decodable", False) and os.environ.get("VIP_JPEG_DEVICE", "1") != "0")
+        self._decode_errs = []      # (first image index, device int32 [n] flags) per device-decoded batch
         self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
         # the prefetch task waits for the decode tasks: it needs a thread of its own (a single-worker pool would deadlock)
         self.prefetcher = ThreadPoolExecutor(max_workers=1)
@@ -143,10 +146,22 @@ class DeviceDataset:
         pending = [self.prefetcher.submit(self._decode_batch, self.paths[i0: i0 + self.batch_size]) for i0 in starts[:depth]]
         for k, i0 in enumerate(starts):
             imgs = pending.pop(0).result()
+            if isinstance(imgs, RawJpegs):
+                imgs.err_sink, imgs.first_index = self._decode_errs, i0
             if k + depth < len(starts):
                 j0 = starts[k + depth]
                 pending.append(self.prefetcher.submit(self._decode_batch, self.paths[j0: j0 + self.batch_size]))
             yield i0, imgs
+
+    def check_decode_errors(self):
+        """Raises for files whose entropy-coded data the device decoder flagged as corrupt (tf.image.decode_jpeg raises
+        InvalidArgumentError for those, dataset/dataset.py:28); one device -> host read per batch, after the pass."""
+        bad = []
+        for i0, err in self._decode_errs:
+            bad += [self.paths[i0 + j] for j in torch.nonzero(err).flatten().tolist()]
+        self._decode_errs.clear()
+        if bad:
+            raise ValueError(f"corrupt JPEG data in {len(bad)} file(s): " + ", ".join(bad[:5]))
 
     def flags_for(self, i0, n, pass_idx):
         """Augmentation decisions of images [i0, i0 + n) of this dataset in TTA pass ``pass_idx``."""

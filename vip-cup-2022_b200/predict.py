@@ -226,6 +226,7 @@ def predict_device(CFG, local_paths, tta, verbose=False, runner_cache=None, inde
     for e in entries:
         outs.append(e["out"].cpu().numpy())
     tm["drain"] = _time.perf_counter() - t0
+    ds.check_decode_errors()
     if prof:
         import sys as _sys
 
