@@ -10,12 +10,9 @@ done <<'S'
 200704 384 768 res lo
 50176 768 768 res lo
 50176 768 1536 res lo
-200704 1152 384 ln
-200704 768 384 ln gelu
-802816 192 192 res lo
-173056 1024 256 se
-692224 512 128 se
-2560000 256 64 se
+200704 384 384
+200704 384 768 relu
+173056 256 2304 relu
+43264 512 4608 relu
 50176 2048 512 se
-173056 256 1024 relu
 S
