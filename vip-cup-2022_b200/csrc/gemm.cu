@@ -274,7 +274,9 @@ struct Cfg {
   static constexpr int kMinBlocks = kDeep ? 1 : 2;
   static constexpr int kChunks = BN / 64;   // 64-column chunks per tile
   // epilogue groups of 4 warps (each covers all 128 rows): one per chunk for the 256-wide deep tiles, otherwise two
-  static constexpr int kGroups = (kDeep && BN == 256) ? 4 : 2;
+  // Two epilogue groups in every configuration: at BN = 256 each group takes two chunks.  Four groups (16 epilogue warps,
+  // 576 threads) cap the kernel at 96 registers with spills and measured 3-11 % slower (profiles/r2_gemm_groups_ab.txt).
+  static constexpr int kGroups = 2;
   static constexpr int kThreads = 64 + 128 * kGroups;
   static constexpr int kTmemCols = 2 * BN;  // 128, 256 or 512: a power of two
   static constexpr int kSmem = kStages * kStageBytes + kCBufs * kCBufBytes + 1024 + 256;
