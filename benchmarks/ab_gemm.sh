@@ -6,14 +6,14 @@ while read -r shape; do
     python benchmarks/one_gemm.py $shape | sed "s/^/new  /"
   done
 done <<'S'
-200704 1152 384 ln
-200704 768 384 ln gelu
-200704 384 384 res lo
-200704 384 768 res lo
-50176 2304 768 ln
-50176 768 1536 res lo
-173056 256 1024 relu
-173056 256 2304 relu
-200704 768 384
-50176 2048 512 se
+173056 1024 256 se
+692224 512 128 se
+2560000 256 64 se
+2560000 64 256 relu
+802816 576 192 ln
+802816 192 192 res lo
+3211264 288 96 ln
+3211264 96 96 res lo
+50176 768 256 ln
+50176 256 256 res lo
 S
